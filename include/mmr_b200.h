@@ -1,0 +1,133 @@
+/*
+ * mmr_b200.h -- C ABI of the B200-native exact-scan library (libmmr_b200.so).
+ *
+ * Drop-in boundary for ONE path of Sabarna07-tech/Multimodal-RAG-for-Image-Text-Search: the flat cosine
+ * nearest-neighbour scan + top-k + text/image fusion + confidence gate behind retrieve_text /
+ * retrieve_images.  The reference has no FFI of its own (it is 100 % Python; the arithmetic lives in the
+ * third-party lancedb/lance Rust crate), so every entry point below cites the reference Python interface
+ * it replaces.  The reference-side binding (a ctypes stub) is shown in INTEGRATION.md; the shipped host
+ * mirror is multimodal-rag-for-image-text-search_b200/store.py (class B200Store == LanceDBStore's duck type).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++ or torch types.  Every function returns an int status
+ *     (MMR_OK == 0); mmr_last_error() gives a thread-local message.  No exception crosses the ABI.
+ *   - Pointers named *_dev are device pointers on the index's device, *_host are host pointers.
+ *   - The caller owns every buffer it passes (rows, queries, outputs, workspace); the library owns only
+ *     the opaque index handle (segment table, device attributes, small staging buffers).
+ *   - Every call that launches work takes the cudaStream_t to launch on (as void*) and is asynchronous
+ *     with respect to the host unless documented otherwise.
+ *   - There is no CPU fallback: on a machine without an sm_100 device the calls fail with MMR_ERR_CUDA.
+ *   - Rows are ordinals into one resident index (< 2^32 rows per GPU); results carry int64 global row ids
+ *     (ordinal + row_base of the shard).  Result order everywhere: score descending, row id ascending.
+ */
+#ifndef MMR_B200_H_
+#define MMR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMR_ABI_VERSION 1
+
+enum mmr_status {
+  MMR_OK = 0,
+  MMR_ERR_INVALID = 1,     /* bad argument */
+  MMR_ERR_CUDA = 2,        /* CUDA runtime / driver error, or no usable sm_100 device */
+  MMR_ERR_UNSUPPORTED = 3, /* valid request this build has no kernel for (e.g. dim not 384/512) */
+  MMR_ERR_WORKSPACE = 4    /* workspace too small */
+};
+
+enum mmr_dtype {
+  MMR_BF16 = 0, /* resident storage chosen by the north star */
+  MMR_F32 = 1,  /* the reference's stored precision (list<float32>) */
+  MMR_F16 = 2
+};
+
+#define MMR_MAX_K 64 /* INDEX_TOPK_TEXT defaults to 50, INDEX_TOPK_IMG to 12 (reference config.py:46-47) */
+
+typedef struct mmr_index mmr_index;
+
+/* Library / error plumbing. */
+int mmr_abi_version(void);
+const char* mmr_last_error(void);
+
+/*
+ * Resident index over caller-owned device rows.
+ *   rows_dev        row-major [n_rows, dim] of `dtype`, 16-byte aligned, rows already L2-normalised
+ *                   (what LanceDBStore._prepare_rows writes, app/storage/lancedb_store.py:71-85).
+ *   seg_offsets_host  [n_segments + 1] ascending row offsets; segment t = rows [off[t], off[t+1]) = the
+ *                   rows of one tenant.  Replaces the per-query `user_id == '...'` filter
+ *                   (lancedb_store.py:107,118,141-144) with prefilter semantics.  NULL / 0 = one segment.
+ *   row_base        added to every row id written out (row-range shard of a larger table).
+ */
+int mmr_index_create(int device, int dim, int dtype, int64_t n_rows, const void* rows_dev,
+                     const int64_t* seg_offsets_host, int32_t n_segments, int64_t row_base, mmr_index** out);
+int mmr_index_destroy(mmr_index* index);
+/* Re-point an existing handle at grown / rewritten rows after an upsert (same dim and dtype). */
+int mmr_index_update(mmr_index* index, int64_t n_rows, const void* rows_dev, const int64_t* seg_offsets_host,
+                     int32_t n_segments);
+
+/*
+ * Loader (L1): fp32 embedding rows -> resident rows of `dtype`, optionally re-normalised exactly like
+ * LanceDBStore._normalize (lancedb_store.py:63-69).  src and dst are device pointers.
+ */
+int mmr_convert_rows_f32(const float* src_dev, void* dst_dev, int dtype, int64_t n_rows, int dim, int normalize,
+                         void* stream);
+/* Same from pageable or pinned HOST memory, streamed through a double-buffered pinned staging area. */
+int mmr_load_rows_f32_host(int device, const float* src_host, void* dst_dev, int dtype, int64_t n_rows, int dim,
+                           int normalize, void* stream);
+
+/*
+ * The scan: LanceDBStore.search_text / search_image (lancedb_store.py:103-123) for a batch of B queries.
+ *   queries_dev     [B, dim] float32, any norm (re-normalised on device as :104 / :115 do).
+ *   query_seg_host  [B] segment id per query, or NULL = every query scans the whole index; -1 = whole index.
+ *   k               max(top_k, 1) of the reference; 1..MMR_MAX_K.
+ *   out_scores_dev  [B, k] float32 cosine similarity, best first; -inf where fewer than k rows exist.
+ *   out_rows_dev    [B, k] int64 row ids, -1 padded.
+ *   workspace_dev   >= mmr_search_workspace_bytes(index, B, k) bytes, ZEROED once before its first use
+ *                   (the library leaves it reusable); not shared between concurrently running searches.
+ */
+size_t mmr_search_workspace_bytes(const mmr_index* index, int32_t B, int32_t k);
+int mmr_search(const mmr_index* index, const float* queries_dev, const int32_t* query_seg_host, int32_t B,
+               int32_t k, float* out_scores_dev, int64_t* out_rows_dev, void* workspace_dev, size_t workspace_bytes,
+               void* stream);
+/*
+ * Same with HOST buffers: copies the queries in, scans, copies results out and synchronises the stream.
+ * This is the call B200Store.search_* makes per request; its time is the end-to-end figure in bench.py.
+ */
+int mmr_search_host(mmr_index* index, const float* queries_host, const int32_t* query_seg_host, int32_t B,
+                    int32_t k, float* out_scores_host, int64_t* out_rows_host, void* stream);
+
+/*
+ * Cross-shard merge (K4): G shard-local results [G, B, k] -> [B, k].  Used after the all-gather when the
+ * index is row-range sharded over GPUs; identical output for every G.
+ */
+int mmr_merge_topk(const float* scores_dev, const int64_t* rows_dev, int32_t G, int32_t B, int32_t k,
+                   float* out_scores_dev, int64_t* out_rows_dev, void* stream);
+
+/*
+ * Fusion + gate (K5): _fuse_results with no rerank scores (reference app/ml/retrieve.py:158-195) and
+ * _confidence_low (app/ml/generate.py:56-60), bit-identical float64 results.
+ *   text_* [B, kt], img_* [B, ki] as written by mmr_search (either may be NULL with k = 0).
+ *   out_combined [B, final_n] f64 combined (z) score; out_score [B, final_n] f64 the item's `score`;
+ *   out_rows [B, final_n] i64 (-1 padded); out_modality [B, final_n] i8 (0 text, 1 image, -1 none);
+ *   out_low_conf [B] u8.
+ */
+int mmr_fuse(const float* text_scores_dev, const int64_t* text_rows_dev, int32_t kt, const float* img_scores_dev,
+             const int64_t* img_rows_dev, int32_t ki, int32_t B, int32_t final_n, double tau,
+             double* out_combined_dev, double* out_score_dev, int64_t* out_rows_dev, int8_t* out_modality_dev,
+             uint8_t* out_low_conf_dev, void* stream);
+
+/* Introspection used by bench.py / tests: launches issued by this library since load, device facts. */
+int64_t mmr_launch_count(void);
+int mmr_device_sm_count(int device, int* out_sms);
+/* Which kernel family the last mmr_search on this thread used: 1 = K1 stream, 2 = K2 umma, 3 = varlen. */
+int mmr_last_kernel(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMR_B200_H_ */

@@ -1,0 +1,17 @@
+"""B200-native exact-scan hot path for Multimodal-RAG (retrieve_text / retrieve_images).
+
+The directory name carries hyphens (it is fixed by the build contract), so import it with
+``importlib.import_module("multimodal-rag-for-image-text-search_b200")`` or through the ``mmr_b200`` alias
+module at the repository root.
+"""
+from . import _native
+from ._native import NativeError
+from .build import build as build_native
+from .index import ResidentIndex, fuse, merge_topk
+from .store import B200Store, VectorRow, make_arrow_table
+from .settings import RetrievalSettings, load_retrieval_settings
+
+__all__ = [
+    "ResidentIndex", "B200Store", "VectorRow", "RetrievalSettings", "load_retrieval_settings", "NativeError",
+    "merge_topk", "fuse", "make_arrow_table", "build_native",
+]

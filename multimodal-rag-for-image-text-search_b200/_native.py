@@ -1,0 +1,67 @@
+"""ctypes binding of libmmr_b200.so (include/mmr_b200.h).  Fails loudly: there is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmmr_b200.so")
+
+MMR_OK = 0
+MMR_BF16, MMR_F32, MMR_F16 = 0, 1, 2
+MMR_MAX_K = 64
+ABI_VERSION = 1
+
+# every symbol include/mmr_b200.h declares: (name, restype, argtypes)
+_i32, _i64, _sz, _p, _f64 = C.c_int32, C.c_int64, C.c_size_t, C.c_void_p, C.c_double
+SYMBOLS = [
+    ("mmr_abi_version", C.c_int, []),
+    ("mmr_last_error", C.c_char_p, []),
+    ("mmr_index_create", C.c_int, [C.c_int, C.c_int, C.c_int, _i64, _p, _p, _i32, _i64, C.POINTER(_p)]),
+    ("mmr_index_destroy", C.c_int, [_p]),
+    ("mmr_index_update", C.c_int, [_p, _i64, _p, _p, _i32]),
+    ("mmr_convert_rows_f32", C.c_int, [_p, _p, C.c_int, _i64, C.c_int, C.c_int, _p]),
+    ("mmr_load_rows_f32_host", C.c_int, [C.c_int, _p, _p, C.c_int, _i64, C.c_int, C.c_int, _p]),
+    ("mmr_search_workspace_bytes", _sz, [_p, _i32, _i32]),
+    ("mmr_search", C.c_int, [_p, _p, _p, _i32, _i32, _p, _p, _p, _sz, _p]),
+    ("mmr_search_host", C.c_int, [_p, _p, _p, _i32, _i32, _p, _p, _p]),
+    ("mmr_merge_topk", C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),
+    ("mmr_fuse", C.c_int, [_p, _p, _i32, _p, _p, _i32, _i32, _i32, _f64, _p, _p, _p, _p, _p, _p]),
+    ("mmr_launch_count", _i64, []),
+    ("mmr_device_sm_count", C.c_int, [C.c_int, C.POINTER(C.c_int)]),
+    ("mmr_last_kernel", C.c_int, []),
+]
+
+
+class NativeError(RuntimeError):
+    """Raised for every non-zero status from the C ABI (propagates like the reference's search errors,
+    app/storage/lancedb_store.py:103-123 has no try/except)."""
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(
+                f"{LIB_PATH} is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). This package has no CPU or eager fallback."
+            )
+        handle = C.CDLL(LIB_PATH)
+        for name, res, args in SYMBOLS:
+            fn = getattr(handle, name)  # AttributeError = ABI mismatch, surface it
+            fn.restype = res
+            fn.argtypes = args
+        if handle.mmr_abi_version() != ABI_VERSION:
+            raise NativeError(f"ABI version mismatch: library {handle.mmr_abi_version()} != binding {ABI_VERSION}")
+        _lib = handle
+    return _lib
+
+
+def check(status: int) -> None:
+    if status != MMR_OK:
+        msg = lib().mmr_last_error()
+        raise NativeError(f"mmr status {status}: {msg.decode() if msg else '?'}")

@@ -1,0 +1,59 @@
+"""Build libmmr_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from typing import List
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libmmr_b200.so")
+SOURCES = ["mmr_b200.cu"]
+ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _nvcc() -> str:
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found: the B200 scan library cannot be built (there is no CPU fallback)")
+    return exe
+
+
+def _deps() -> List[str]:
+    out = [os.path.join(HERE, "..", "include", "mmr_b200.h")]
+    for name in os.listdir(CSRC):
+        if name.endswith((".cu", ".cuh", ".h")):
+            out.append(os.path.join(CSRC, name))
+    return out
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(p) > t for p in _deps() if os.path.exists(p))
+
+
+def build(force: bool = False, verbose: bool = False, extra: List[str] | None = None) -> str:
+    """Compile csrc/*.cu -> libmmr_b200.so.  Returns the library path."""
+    if not force and not needs_build():
+        return LIB
+    defines = ["-DMMR_WITH_UMMA"] if os.path.exists(os.path.join(CSRC, "scan_umma.cuh")) else []
+    cmd = [
+        _nvcc(), *ARCH_FLAGS, "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+        *defines, *(extra or []), "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES],
+    ]
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose and (res.stdout or res.stderr):
+        print(res.stdout + res.stderr, file=sys.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,205 @@
+// Small kernels either side of the scan: the resident-index loader (L1), the cross-shard merge (K4)
+// and the fusion / confidence-gate epilogue (K5).
+#pragma once
+#include "common.cuh"
+#include "topk.cuh"
+
+namespace mmr {
+
+// ------------------------------------------------------------------------------------------------
+// L1 -- fp32 rows (the reference's list<float32> embedding column, app/storage/lancedb_store.py:33-44)
+// -> resident bf16 / fp16 / fp32 rows.  One warp per row.  normalize != 0 re-applies
+// LanceDBStore._normalize (:63-69, f32: x / ||x|| unless ||x|| <= 0) before the narrowing cast, which is
+// what _prepare_rows (:71-85) does on the write path.
+// ------------------------------------------------------------------------------------------------
+template <typename E>
+__device__ __forceinline__ E cast_elem(float x);
+template <>
+__device__ __forceinline__ __nv_bfloat16 cast_elem<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+template <>
+__device__ __forceinline__ __half cast_elem<__half>(float x) { return __float2half_rn(x); }
+template <>
+__device__ __forceinline__ float cast_elem<float>(float x) { return x; }
+
+template <typename E>
+__global__ void convert_rows_kernel(const float* __restrict__ src, E* __restrict__ dst, int64_t n_rows, int dim,
+                                    int normalize) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = int64_t(gridDim.x) * (blockDim.x >> 5);
+  for (int64_t row = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_rows; row += warps) {
+    const float* s = src + row * dim;
+    E* d = dst + row * dim;
+    float inv = 1.f;
+    bool scale = false;
+    if (normalize) {
+      float ss = 0.f;
+      for (int i = lane; i < dim; i += 32) {
+        const float x = s[i];
+        ss = fmaf(x, x, ss);
+      }
+      ss = warp_allreduce_sum(ss);
+      const float nrm = sqrtf(ss);
+      scale = nrm > 0.f;
+      inv = nrm;
+    }
+    for (int i = lane; i < dim; i += 32) {
+      const float x = s[i];
+      d[i] = cast_elem<E>(scale ? x / inv : x);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 -- merge G shard-local top-k lists into one.  Inputs are what each shard's scan wrote:
+// scores [G, B, k] f32 and rows [G, B, k] i64 (global ordinals, -1 = empty).  One warp per query.
+// Same total order as everywhere else: (score desc, row asc); result is independent of G.
+// ------------------------------------------------------------------------------------------------
+template <int KPL>
+__global__ void merge_shards_kernel(const float* __restrict__ scores, const int64_t* __restrict__ rows, int G, int B,
+                                    int k, float* __restrict__ out_scores, int64_t* __restrict__ out_rows) {
+  const int lane = threadIdx.x & 31;
+  const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (qi >= B) return;
+  WarpTopK<KPL> m;
+  m.clear();
+  uint64_t thr = 0ull;
+  const int per = k;  // entries per shard for this query
+  const int total = G * per;
+  for (int i0 = 0; i0 < total; i0 += 32) {
+    const int i = i0 + lane;
+    bool valid = i < total;
+    uint64_t key = 0ull;
+    if (valid) {
+      const int g = i / per, j = i % per;
+      const size_t o = (size_t(g) * B + qi) * k + j;
+      const int64_t r = rows[o];
+      valid = r >= 0;
+      if (valid) key = make_key(scores[o], uint32_t(r));
+    }
+    thr = m.offer(key, valid, thr, k, lane);
+  }
+#pragma unroll
+  for (int j = 0; j < KPL; ++j) {
+    const int pos = j * 32 + lane;
+    if (pos < k) {
+      const uint64_t key = m.key[j];
+      out_scores[size_t(qi) * k + pos] = key ? key_score(key) : -INFINITY;
+      out_rows[size_t(qi) * k + pos] = key ? int64_t(key_row(key)) : int64_t(-1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5 -- text+image score fusion and the CONFIDENCE_TAU gate for the rerank-off path.
+// Follows _z_scores / _fuse_results (reference app/ml/retrieve.py:186-195, 158-183) and _confidence_low
+// (app/ml/generate.py:56-60) operation by operation so the result is bit-identical to the reference:
+//   v_i      = 1.0 - double(f32(1) - cos_i)          (_format_results, lancedb_store.py:130-131)
+//   arr      = float32(v)                             (np.array(numeric, dtype=np.float32))
+//   mean,std = numpy float32 mean / population std:   pairwise sum with 8 accumulators for n >= 8,
+//              plain left-to-right for n < 8, divide by n in f32, sqrt in f32
+//   z_i      = (v_i - double(mean)) / double(std)     in float64; all 0.0 when std == 0
+//   combined = z_i  (np.mean of a one-element list), items = text then image, stable sort descending,
+//   cut to final_n; low_conf = no items or max(combined) < tau.
+// One thread per query (k <= 64 per modality; the work is ~200 flops).  No FMA contraction anywhere.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float np_pairwise_sum_f32(const float* a, int n) {
+  if (n < 8) {
+    float res = 0.f;
+    for (int i = 0; i < n; ++i) res = __fadd_rn(res, a[i]);
+    return res;
+  }
+  float r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = a[j];
+  int i = 8;
+  const int lim = n - (n % 8);
+  for (; i < lim; i += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], a[i + j]);
+  }
+  float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                        __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+  for (; i < n; ++i) res = __fadd_rn(res, a[i]);
+  return res;
+}
+
+constexpr int FUSE_MAXK = 64;
+
+// z-scores of n cosine scores -> z[0..n) (float64) ; v (the python-float score) also returned
+__device__ __forceinline__ void np_z_scores(const float* cos, int n, double* v, double* z) {
+  float arr[FUSE_MAXK], sq[FUSE_MAXK];
+  for (int i = 0; i < n; ++i) {
+    const float d = __fsub_rn(1.0f, cos[i]);
+    v[i] = __dsub_rn(1.0, double(d));
+    arr[i] = __double2float_rn(v[i]);
+  }
+  const float fn = float(n);
+  const float mean = __fdiv_rn(np_pairwise_sum_f32(arr, n), fn);
+  for (int i = 0; i < n; ++i) {
+    const float x = __fsub_rn(arr[i], mean);
+    sq[i] = __fmul_rn(x, x);
+  }
+  const float var = __fdiv_rn(np_pairwise_sum_f32(sq, n), fn);
+  const float sd = __fsqrt_rn(var);
+  if (sd == 0.f) {
+    for (int i = 0; i < n; ++i) z[i] = 0.0;
+  } else {
+    const double dm = double(mean), ds = double(sd);
+    for (int i = 0; i < n; ++i) z[i] = __ddiv_rn(__dsub_rn(v[i], dm), ds);
+  }
+}
+
+__global__ void fuse_kernel(const float* __restrict__ text_scores, const int64_t* __restrict__ text_rows, int kt,
+                            const float* __restrict__ img_scores, const int64_t* __restrict__ img_rows, int ki, int B,
+                            int final_n, double tau, double* __restrict__ out_combined,
+                            double* __restrict__ out_score, int64_t* __restrict__ out_rows,
+                            int8_t* __restrict__ out_modality, uint8_t* __restrict__ out_low_conf) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= B) return;
+  double v[2 * FUSE_MAXK], z[2 * FUSE_MAXK];
+  // valid hits are a prefix (the scan pads with row = -1 at the end)
+  int nt = 0, ni = 0;
+  if (text_rows) {
+    while (nt < kt && text_rows[size_t(qi) * kt + nt] >= 0) ++nt;
+  }
+  if (img_rows) {
+    while (ni < ki && img_rows[size_t(qi) * ki + ni] >= 0) ++ni;
+  }
+  if (nt) np_z_scores(text_scores + size_t(qi) * kt, nt, v, z);
+  if (ni) np_z_scores(img_scores + size_t(qi) * ki, ni, v + nt, z + nt);
+  const int n = nt + ni;
+  // stable selection of the final_n largest combined scores (n <= 128, final_n small)
+  unsigned long long taken_lo = 0ull, taken_hi = 0ull;
+  double best0 = 0.0;
+  for (int o = 0; o < final_n; ++o) {
+    int bi = -1;
+    double bz = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const bool taken = i < 64 ? ((taken_lo >> i) & 1ull) : ((taken_hi >> (i - 64)) & 1ull);
+      if (taken) continue;
+      if (bi < 0 || z[i] > bz) {  // strict > keeps the earliest among equals = stable descending sort
+        bi = i;
+        bz = z[i];
+      }
+    }
+    const size_t oo = size_t(qi) * final_n + o;
+    if (bi < 0) {
+      out_combined[oo] = 0.0;
+      out_score[oo] = 0.0;
+      out_rows[oo] = -1;
+      out_modality[oo] = -1;
+      continue;
+    }
+    if (bi < 64) taken_lo |= 1ull << bi; else taken_hi |= 1ull << (bi - 64);
+    if (o == 0) best0 = bz;
+    out_combined[oo] = bz;
+    out_score[oo] = v[bi];
+    const bool is_text = bi < nt;
+    out_rows[oo] = is_text ? text_rows[size_t(qi) * kt + bi] : img_rows[size_t(qi) * ki + (bi - nt)];
+    out_modality[oo] = is_text ? 0 : 1;
+  }
+  // _confidence_low looks at the returned items only (generate.py:56-60)
+  out_low_conf[qi] = (n == 0 || final_n <= 0) ? 1 : (best0 < tau ? 1 : 0);
+}
+
+}  // namespace mmr

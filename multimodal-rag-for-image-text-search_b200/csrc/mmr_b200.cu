@@ -1,0 +1,519 @@
+// libmmr_b200.so -- C ABI (include/mmr_b200.h) over the sm_100a scan kernels.
+// Host side: argument checks, planning (which kernel, grid, workspace carve-up), launches.
+#include "../../include/mmr_b200.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "aux_kernels.cuh"
+#include "common.cuh"
+#include "scan_stream.cuh"
+#ifdef MMR_WITH_UMMA
+#include "scan_umma.cuh"
+#endif
+
+using namespace mmr;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static thread_local int g_last_kernel = 0;
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                                \
+  do {                                                                                                \
+    cudaError_t e_ = (expr);                                                                          \
+    if (e_ != cudaSuccess) return fail(MMR_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                                       __FILE__, __LINE__);                                           \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------ index
+struct mmr_index {
+  int device = 0;
+  int dim = 0;
+  int dtype = MMR_BF16;
+  int64_t n_rows = 0;
+  const void* rows = nullptr;
+  int64_t row_base = 0;
+  std::vector<int64_t> seg;  // [n_segments + 1]
+  int sm_count = 0;
+  // small staging for mmr_search_host
+  float* h_q = nullptr;
+  float* d_q = nullptr;
+  float* d_scores = nullptr;
+  int64_t* d_rows = nullptr;
+  float* h_scores = nullptr;
+  int64_t* h_rows = nullptr;
+  void* d_ws = nullptr;
+  size_t ws_bytes = 0;
+  int cap_b = 0, cap_k = 0;
+#ifdef MMR_WITH_UMMA
+  UmmaIndexState umma;
+#endif
+};
+
+static int elem_bytes(int dtype) { return dtype == MMR_F32 ? 4 : 2; }
+
+static int set_segments(mmr_index* ix, const int64_t* seg, int32_t nseg) {
+  ix->seg.clear();
+  if (seg == nullptr || nseg <= 0) {
+    ix->seg = {0, ix->n_rows};
+    return MMR_OK;
+  }
+  ix->seg.assign(seg, seg + nseg + 1);
+  if (ix->seg.front() < 0 || ix->seg.back() > ix->n_rows) return fail(MMR_ERR_INVALID, "segment offsets out of range");
+  for (int i = 0; i < nseg; ++i)
+    if (ix->seg[i] > ix->seg[i + 1]) return fail(MMR_ERR_INVALID, "segment offsets must be ascending");
+  return MMR_OK;
+}
+
+extern "C" int mmr_abi_version(void) { return MMR_ABI_VERSION; }
+extern "C" const char* mmr_last_error(void) { return g_err.c_str(); }
+extern "C" int64_t mmr_launch_count(void) { return g_launches.load(); }
+extern "C" int mmr_last_kernel(void) { return g_last_kernel; }
+
+extern "C" int mmr_device_sm_count(int device, int* out_sms) {
+  if (!out_sms) return fail(MMR_ERR_INVALID, "out_sms is NULL");
+  CUDA_TRY(cudaDeviceGetAttribute(out_sms, cudaDevAttrMultiProcessorCount, device));
+  return MMR_OK;
+}
+
+extern "C" int mmr_index_create(int device, int dim, int dtype, int64_t n_rows, const void* rows_dev,
+                                const int64_t* seg_offsets_host, int32_t n_segments, int64_t row_base,
+                                mmr_index** out) {
+  if (!out) return fail(MMR_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (dtype != MMR_BF16 && dtype != MMR_F32 && dtype != MMR_F16) return fail(MMR_ERR_INVALID, "unknown dtype %d", dtype);
+  if (dim <= 0 || n_rows < 0) return fail(MMR_ERR_INVALID, "bad shape [%lld, %d]", (long long)n_rows, dim);
+  if (n_rows >= (int64_t(1) << 32)) return fail(MMR_ERR_UNSUPPORTED, "at most 2^32-1 rows per resident index");
+  if (n_rows > 0 && rows_dev == nullptr) return fail(MMR_ERR_INVALID, "rows_dev is NULL");
+  if ((reinterpret_cast<uintptr_t>(rows_dev) & 15) != 0) return fail(MMR_ERR_INVALID, "rows_dev must be 16-byte aligned");
+  if (dim != 384 && dim != 512)
+    return fail(MMR_ERR_UNSUPPORTED, "dim %d: kernels are built for 384 (MiniLM) and 512 (CLIP)", dim);
+  int major = 0, minor = 0, sms = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  CUDA_TRY(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  if (major != 10) return fail(MMR_ERR_CUDA, "device %d is sm_%d%d; this library is sm_100a only", device, major, minor);
+  mmr_index* ix = new mmr_index();
+  ix->device = device;
+  ix->dim = dim;
+  ix->dtype = dtype;
+  ix->n_rows = n_rows;
+  ix->rows = rows_dev;
+  ix->row_base = row_base;
+  ix->sm_count = sms;
+  int rc = set_segments(ix, seg_offsets_host, n_segments);
+  if (rc != MMR_OK) {
+    delete ix;
+    return rc;
+  }
+  *out = ix;
+  return MMR_OK;
+}
+
+extern "C" int mmr_index_update(mmr_index* ix, int64_t n_rows, const void* rows_dev, const int64_t* seg, int32_t nseg) {
+  if (!ix) return fail(MMR_ERR_INVALID, "index is NULL");
+  if (n_rows < 0 || n_rows >= (int64_t(1) << 32)) return fail(MMR_ERR_INVALID, "bad n_rows");
+  if (n_rows > 0 && rows_dev == nullptr) return fail(MMR_ERR_INVALID, "rows_dev is NULL");
+  if ((reinterpret_cast<uintptr_t>(rows_dev) & 15) != 0) return fail(MMR_ERR_INVALID, "rows_dev must be 16-byte aligned");
+  ix->n_rows = n_rows;
+  ix->rows = rows_dev;
+#ifdef MMR_WITH_UMMA
+  ix->umma.valid = false;
+#endif
+  return set_segments(ix, seg, nseg);
+}
+
+static void free_staging(mmr_index* ix) {
+  if (ix->h_q) cudaFreeHost(ix->h_q);
+  if (ix->h_scores) cudaFreeHost(ix->h_scores);
+  if (ix->h_rows) cudaFreeHost(ix->h_rows);
+  if (ix->d_q) cudaFree(ix->d_q);
+  if (ix->d_scores) cudaFree(ix->d_scores);
+  if (ix->d_rows) cudaFree(ix->d_rows);
+  if (ix->d_ws) cudaFree(ix->d_ws);
+  ix->h_q = ix->d_q = ix->d_scores = ix->h_scores = nullptr;
+  ix->h_rows = ix->d_rows = nullptr;
+  ix->d_ws = nullptr;
+  ix->cap_b = ix->cap_k = 0;
+}
+
+extern "C" int mmr_index_destroy(mmr_index* ix) {
+  if (!ix) return MMR_OK;
+  cudaSetDevice(ix->device);
+  free_staging(ix);
+  delete ix;
+  return MMR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ loader
+template <typename E>
+static int launch_convert(const float* src, void* dst, int64_t n, int dim, int normalize, cudaStream_t st) {
+  if (n == 0) return MMR_OK;
+  const int threads = 256;
+  const int64_t blocks = std::min<int64_t>((n + 7) / 8, 148 * 16);
+  convert_rows_kernel<E><<<(unsigned)blocks, threads, 0, st>>>(src, reinterpret_cast<E*>(dst), n, dim, normalize);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return MMR_OK;
+}
+
+extern "C" int mmr_convert_rows_f32(const float* src_dev, void* dst_dev, int dtype, int64_t n_rows, int dim,
+                                    int normalize, void* stream) {
+  if (n_rows < 0 || dim <= 0) return fail(MMR_ERR_INVALID, "bad shape");
+  if (n_rows > 0 && (!src_dev || !dst_dev)) return fail(MMR_ERR_INVALID, "NULL buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (dtype) {
+    case MMR_BF16: return launch_convert<__nv_bfloat16>(src_dev, dst_dev, n_rows, dim, normalize, st);
+    case MMR_F16: return launch_convert<__half>(src_dev, dst_dev, n_rows, dim, normalize, st);
+    case MMR_F32: return launch_convert<float>(src_dev, dst_dev, n_rows, dim, normalize, st);
+  }
+  return fail(MMR_ERR_INVALID, "unknown dtype %d", dtype);
+}
+
+extern "C" int mmr_load_rows_f32_host(int device, const float* src_host, void* dst_dev, int dtype, int64_t n_rows,
+                                      int dim, int normalize, void* stream) {
+  if (n_rows < 0 || dim <= 0) return fail(MMR_ERR_INVALID, "bad shape");
+  if (n_rows == 0) return MMR_OK;
+  if (!src_host || !dst_dev) return fail(MMR_ERR_INVALID, "NULL buffer");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t chunk_rows = std::max<int64_t>(1, (int64_t(64) << 20) / (int64_t(dim) * 4));  // 64 MiB chunks
+  const size_t chunk_bytes = size_t(chunk_rows) * dim * 4;
+  float* h[2] = {nullptr, nullptr};
+  float* d[2] = {nullptr, nullptr};
+  cudaEvent_t done[2];
+  int rc = MMR_OK;
+  auto cleanup = [&]() {
+    for (int i = 0; i < 2; ++i) {
+      if (h[i]) cudaFreeHost(h[i]);
+      if (d[i]) cudaFree(d[i]);
+    }
+  };
+  for (int i = 0; i < 2; ++i) {
+    if (cudaMallocHost(&h[i], chunk_bytes) != cudaSuccess || cudaMalloc(&d[i], chunk_bytes) != cudaSuccess) {
+      cleanup();
+      return fail(MMR_ERR_CUDA, "staging allocation of %zu bytes failed", chunk_bytes);
+    }
+    cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
+  }
+  const int eb = elem_bytes(dtype);
+  int slot = 0;
+  for (int64_t r0 = 0; r0 < n_rows && rc == MMR_OK; r0 += chunk_rows, slot ^= 1) {
+    const int64_t nr = std::min(chunk_rows, n_rows - r0);
+    cudaEventSynchronize(done[slot]);  // staging slot free again
+    memcpy(h[slot], src_host + r0 * dim, size_t(nr) * dim * 4);
+    if (cudaMemcpyAsync(d[slot], h[slot], size_t(nr) * dim * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+      rc = fail(MMR_ERR_CUDA, "H2D copy failed");
+      break;
+    }
+    rc = mmr_convert_rows_f32(d[slot], static_cast<uint8_t*>(dst_dev) + size_t(r0) * dim * eb, dtype, nr, dim,
+                              normalize, st);
+    cudaEventRecord(done[slot], st);
+  }
+  cudaStreamSynchronize(st);
+  for (int i = 0; i < 2; ++i) cudaEventDestroy(done[i]);
+  cleanup();
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ K1 launch
+typedef void (*stream_kernel_t)(const StreamParams);
+
+template <typename E, int D, int NQ, int KPL>
+static int launch_stream_t(const StreamParams& p, int grid, cudaStream_t st) {
+  using C = StreamCfg<E, D, NQ, KPL>;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    CUDA_TRY(cudaFuncSetAttribute(scan_stream_kernel<E, D, NQ, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C::SMEM_BYTES));
+    attr_set[dev] = true;
+  }
+  scan_stream_kernel<E, D, NQ, KPL><<<grid, K1_THREADS, C::SMEM_BYTES, st>>>(p);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return MMR_OK;
+}
+
+template <typename E, int D>
+static int launch_stream_ed(const StreamParams& p, int nq_pad, int kpl, int grid, cudaStream_t st) {
+#define MMR_CASE(NQ_, KPL_) \
+  if (nq_pad == NQ_ && kpl == KPL_) return launch_stream_t<E, D, NQ_, KPL_>(p, grid, st);
+  MMR_CASE(1, 1) MMR_CASE(1, 2) MMR_CASE(2, 1) MMR_CASE(2, 2) MMR_CASE(4, 1) MMR_CASE(4, 2)
+#undef MMR_CASE
+  return fail(MMR_ERR_UNSUPPORTED, "no stream kernel for nq=%d kpl=%d", nq_pad, kpl);
+}
+
+static int launch_stream(const mmr_index* ix, const StreamParams& p, int nq_pad, int kpl, int grid, cudaStream_t st) {
+  const int key = ix->dtype * 1000 + ix->dim;
+  switch (key) {
+    case MMR_BF16 * 1000 + 512: return launch_stream_ed<__nv_bfloat16, 512>(p, nq_pad, kpl, grid, st);
+    case MMR_BF16 * 1000 + 384: return launch_stream_ed<__nv_bfloat16, 384>(p, nq_pad, kpl, grid, st);
+    case MMR_F16 * 1000 + 512: return launch_stream_ed<__half, 512>(p, nq_pad, kpl, grid, st);
+    case MMR_F16 * 1000 + 384: return launch_stream_ed<__half, 384>(p, nq_pad, kpl, grid, st);
+    case MMR_F32 * 1000 + 512: return launch_stream_ed<float, 512>(p, nq_pad, kpl, grid, st);
+    case MMR_F32 * 1000 + 384: return launch_stream_ed<float, 384>(p, nq_pad, kpl, grid, st);
+  }
+  return fail(MMR_ERR_UNSUPPORTED, "no stream kernel for dtype %d dim %d", ix->dtype, ix->dim);
+}
+
+static int rows_per_stage(int dtype) { return dtype == MMR_F32 ? 4 : 8; }
+
+// ------------------------------------------------------------------------------------------------ planning
+// Workspace layout (bytes):
+//   [0, 256)                          control block (ticket counter at +0)
+//   [256, 256 + PART)                 partial top-k keys  (uniform: grid*4*k u64; varlen: n_items*k u64)
+//   then (varlen only)                ScanItem[n_items], int32 item_off[B+1]
+static constexpr size_t WS_CTRL = 256;
+static constexpr int VARLEN_ITEMS_PER_WARP = 8;
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int max_varlen_items(const mmr_index* ix, int B) { return ix->sm_count * K1_NW * VARLEN_ITEMS_PER_WARP + 2 * B + 64; }
+
+extern "C" size_t mmr_search_workspace_bytes(const mmr_index* ix, int32_t B, int32_t k) {
+  if (!ix || B <= 0 || k <= 0) return 0;
+  const size_t kk = size_t(std::min<int32_t>(k, MMR_MAX_K));
+  const size_t uniform = size_t(ix->sm_count) * 4 * kk * 8;
+  const size_t items = size_t(max_varlen_items(ix, B));
+  const size_t varlen = align_up(items * kk * 8, 256) + align_up(items * sizeof(ScanItem), 256) +
+                        align_up(size_t(B + 1) * 4, 256);
+  size_t total = WS_CTRL + align_up(std::max(uniform, varlen), 256);
+#ifdef MMR_WITH_UMMA
+  total += umma_workspace_bytes(ix->sm_count, ix->dim, B, int(kk));
+#endif
+  return total;
+}
+
+static int search_uniform_stream(const mmr_index* ix, const float* q, int B, int k, uint32_t r0, uint32_t r1,
+                                 float* out_s, int64_t* out_r, uint8_t* ws, cudaStream_t st) {
+  const int kpl = k <= 32 ? 1 : 2;
+  const int R = rows_per_stage(ix->dtype);
+  const int64_t nchunks = (int64_t(r1) - r0 + R - 1) / R;
+  int grid = int(std::min<int64_t>(ix->sm_count, std::max<int64_t>(1, (nchunks + K1_NW - 1) / K1_NW)));
+  for (int q0 = 0; q0 < B; q0 += 4) {
+    const int nq = std::min(4, B - q0);
+    const int nq_pad = nq == 3 ? 4 : nq;
+    StreamParams p{};
+    p.rows = ix->rows;
+    p.queries = q;
+    p.q_first = q0;
+    p.nq = nq;
+    p.k = k;
+    p.row_begin = r0;
+    p.row_end = r1;
+    p.partial = reinterpret_cast<uint64_t*>(ws + WS_CTRL);
+    p.ticket = reinterpret_cast<unsigned int*>(ws);
+    p.out_scores = out_s;
+    p.out_rows = out_r;
+    p.row_base = ix->row_base;
+    p.items = nullptr;
+    p.n_items = 0;
+    int rc = launch_stream(ix, p, nq_pad, kpl, grid, st);
+    if (rc != MMR_OK) return rc;
+  }
+  g_last_kernel = 1;
+  return MMR_OK;
+}
+
+static int search_varlen_stream(const mmr_index* ix, const float* q, const std::vector<std::pair<uint32_t, uint32_t>>& ranges,
+                                int k, float* out_s, int64_t* out_r, uint8_t* ws, size_t ws_bytes, cudaStream_t st) {
+  const int B = int(ranges.size());
+  const int kpl = k <= 32 ? 1 : 2;
+  const int R = rows_per_stage(ix->dtype);
+  int64_t total_rows = 0;
+  for (auto& r : ranges) total_rows += int64_t(r.second) - r.first;
+  const int twarps = ix->sm_count * K1_NW;
+  const int64_t target = int64_t(twarps) * VARLEN_ITEMS_PER_WARP;
+  int64_t item_rows = std::max<int64_t>(64, (total_rows + target - 1) / target);
+  item_rows = (item_rows + R - 1) / R * R;
+  std::vector<ScanItem> items;
+  std::vector<int32_t> off(B + 1, 0);
+  for (int b = 0; b < B; ++b) {
+    off[b] = int32_t(items.size());
+    for (int64_t s = ranges[b].first; s < int64_t(ranges[b].second); s += item_rows) {
+      ScanItem it;
+      it.row_begin = uint32_t(s);
+      it.row_end = uint32_t(std::min<int64_t>(s + item_rows, ranges[b].second));
+      it.query = b;
+      it.pad = 0;
+      items.push_back(it);
+    }
+  }
+  off[B] = int32_t(items.size());
+  const int n_items = int(items.size());
+  if (n_items > max_varlen_items(ix, B)) return fail(MMR_ERR_WORKSPACE, "varlen plan produced %d items", n_items);
+  const size_t part_bytes = align_up(size_t(std::max(n_items, 1)) * k * 8, 256);
+  const size_t item_bytes = align_up(size_t(std::max(n_items, 1)) * sizeof(ScanItem), 256);
+  const size_t off_bytes = align_up(size_t(B + 1) * 4, 256);
+  if (WS_CTRL + part_bytes + item_bytes + off_bytes > ws_bytes) return fail(MMR_ERR_WORKSPACE, "workspace too small");
+  uint64_t* d_part = reinterpret_cast<uint64_t*>(ws + WS_CTRL);
+  ScanItem* d_items = reinterpret_cast<ScanItem*>(ws + WS_CTRL + part_bytes);
+  int32_t* d_off = reinterpret_cast<int32_t*>(ws + WS_CTRL + part_bytes + item_bytes);
+  if (n_items > 0) CUDA_TRY(cudaMemcpyAsync(d_items, items.data(), size_t(n_items) * sizeof(ScanItem), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_off, off.data(), size_t(B + 1) * 4, cudaMemcpyHostToDevice, st));
+  // pageable sources: the copies above are staged before returning, the vectors may die after this call
+  if (n_items > 0) {
+    StreamParams p{};
+    p.rows = ix->rows;
+    p.queries = q;
+    p.q_first = 0;
+    p.nq = 1;
+    p.k = k;
+    p.partial = d_part;
+    p.ticket = reinterpret_cast<unsigned int*>(ws);
+    p.row_base = ix->row_base;
+    p.items = d_items;
+    p.n_items = n_items;
+    const int grid = int(std::min<int64_t>(ix->sm_count, (n_items + K1_NW - 1) / K1_NW));
+    int rc = launch_stream(ix, p, 1, kpl, grid, st);
+    if (rc != MMR_OK) return rc;
+  }
+  const int wpb = 4;
+  if (kpl == 1)
+    merge_items_kernel<1><<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(d_part, d_off, B, k, out_s, out_r, ix->row_base);
+  else
+    merge_items_kernel<2><<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(d_part, d_off, B, k, out_s, out_r, ix->row_base);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  g_last_kernel = 3;
+  return MMR_OK;
+}
+
+extern "C" int mmr_search(const mmr_index* ix, const float* queries_dev, const int32_t* query_seg_host, int32_t B,
+                          int32_t k, float* out_scores_dev, int64_t* out_rows_dev, void* workspace_dev,
+                          size_t workspace_bytes, void* stream) {
+  if (!ix) return fail(MMR_ERR_INVALID, "index is NULL");
+  if (B <= 0) return fail(MMR_ERR_INVALID, "B must be >= 1");
+  if (k < 1 || k > MMR_MAX_K) return fail(MMR_ERR_INVALID, "k must be in [1, %d]", MMR_MAX_K);
+  if (!queries_dev || !out_scores_dev || !out_rows_dev || !workspace_dev) return fail(MMR_ERR_INVALID, "NULL buffer");
+  if (workspace_bytes < mmr_search_workspace_bytes(ix, B, k)) return fail(MMR_ERR_WORKSPACE, "workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
+  const int nseg = int(ix->seg.size()) - 1;
+
+  // row range of every query
+  std::vector<std::pair<uint32_t, uint32_t>> ranges(B);
+  bool uniform = true;
+  for (int b = 0; b < B; ++b) {
+    const int s = query_seg_host ? query_seg_host[b] : -1;
+    if (s < -1 || s >= nseg) return fail(MMR_ERR_INVALID, "query %d: segment %d out of range [0, %d)", b, s, nseg);
+    ranges[b] = s < 0 ? std::make_pair(uint32_t(0), uint32_t(ix->n_rows))
+                      : std::make_pair(uint32_t(ix->seg[s]), uint32_t(ix->seg[s + 1]));
+    if (ranges[b] != ranges[0]) uniform = false;
+  }
+  if (uniform) {
+#ifdef MMR_WITH_UMMA
+    if (umma_preferred(ix->dtype, ix->dim, B, k, int64_t(ranges[0].second) - ranges[0].first)) {
+      int rc = umma_search(ix->umma, ix->rows, ix->n_rows, ix->dim, ix->sm_count, queries_dev, B, k, ranges[0].first,
+                           ranges[0].second, ix->row_base, out_scores_dev, out_rows_dev,
+                           ws + mmr_search_workspace_bytes(ix, B, k) - umma_workspace_bytes(ix->sm_count, ix->dim, B, k),
+                           st, g_err);
+      if (rc == MMR_OK) {
+        g_launches += umma_launches_per_search();
+        g_last_kernel = 2;
+      }
+      return rc;
+    }
+#endif
+    return search_uniform_stream(ix, queries_dev, B, k, ranges[0].first, ranges[0].second, out_scores_dev,
+                                 out_rows_dev, ws, st);
+  }
+  return search_varlen_stream(ix, queries_dev, ranges, k, out_scores_dev, out_rows_dev, ws, workspace_bytes, st);
+}
+
+static int ensure_staging(mmr_index* ix, int B, int k) {
+  if (B <= ix->cap_b && k <= ix->cap_k) return MMR_OK;
+  free_staging(ix);
+  const int cb = std::max(B, 8), ck = std::max(k, 16);
+  CUDA_TRY(cudaMallocHost(&ix->h_q, size_t(cb) * ix->dim * 4));
+  CUDA_TRY(cudaMallocHost(&ix->h_scores, size_t(cb) * ck * 4));
+  CUDA_TRY(cudaMallocHost(&ix->h_rows, size_t(cb) * ck * 8));
+  CUDA_TRY(cudaMalloc(&ix->d_q, size_t(cb) * ix->dim * 4));
+  CUDA_TRY(cudaMalloc(&ix->d_scores, size_t(cb) * ck * 4));
+  CUDA_TRY(cudaMalloc(&ix->d_rows, size_t(cb) * ck * 8));
+  ix->ws_bytes = mmr_search_workspace_bytes(ix, cb, ck);
+  CUDA_TRY(cudaMalloc(&ix->d_ws, ix->ws_bytes));
+  CUDA_TRY(cudaMemset(ix->d_ws, 0, ix->ws_bytes));
+  ix->cap_b = cb;
+  ix->cap_k = ck;
+  return MMR_OK;
+}
+
+extern "C" int mmr_search_host(mmr_index* ix, const float* queries_host, const int32_t* query_seg_host, int32_t B,
+                               int32_t k, float* out_scores_host, int64_t* out_rows_host, void* stream) {
+  if (!ix) return fail(MMR_ERR_INVALID, "index is NULL");
+  if (B <= 0) return fail(MMR_ERR_INVALID, "B must be >= 1");
+  if (k < 1 || k > MMR_MAX_K) return fail(MMR_ERR_INVALID, "k must be in [1, %d]", MMR_MAX_K);
+  if (!queries_host || !out_scores_host || !out_rows_host) return fail(MMR_ERR_INVALID, "NULL buffer");
+  CUDA_TRY(cudaSetDevice(ix->device));
+  int rc = ensure_staging(ix, B, k);
+  if (rc != MMR_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  memcpy(ix->h_q, queries_host, size_t(B) * ix->dim * 4);
+  CUDA_TRY(cudaMemcpyAsync(ix->d_q, ix->h_q, size_t(B) * ix->dim * 4, cudaMemcpyHostToDevice, st));
+  rc = mmr_search(ix, ix->d_q, query_seg_host, B, k, ix->d_scores, ix->d_rows, ix->d_ws, ix->ws_bytes, st);
+  if (rc != MMR_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(ix->h_scores, ix->d_scores, size_t(B) * k * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(ix->h_rows, ix->d_rows, size_t(B) * k * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  memcpy(out_scores_host, ix->h_scores, size_t(B) * k * 4);
+  memcpy(out_rows_host, ix->h_rows, size_t(B) * k * 8);
+  return MMR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ K4 / K5
+extern "C" int mmr_merge_topk(const float* scores_dev, const int64_t* rows_dev, int32_t G, int32_t B, int32_t k,
+                              float* out_scores_dev, int64_t* out_rows_dev, void* stream) {
+  if (G <= 0 || B <= 0) return fail(MMR_ERR_INVALID, "G and B must be >= 1");
+  if (k < 1 || k > MMR_MAX_K) return fail(MMR_ERR_INVALID, "k must be in [1, %d]", MMR_MAX_K);
+  if (!scores_dev || !rows_dev || !out_scores_dev || !out_rows_dev) return fail(MMR_ERR_INVALID, "NULL buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int wpb = 4;
+  const int blocks = (B + wpb - 1) / wpb;
+  if (k <= 32)
+    merge_shards_kernel<1><<<blocks, wpb * 32, 0, st>>>(scores_dev, rows_dev, G, B, k, out_scores_dev, out_rows_dev);
+  else
+    merge_shards_kernel<2><<<blocks, wpb * 32, 0, st>>>(scores_dev, rows_dev, G, B, k, out_scores_dev, out_rows_dev);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return MMR_OK;
+}
+
+extern "C" int mmr_fuse(const float* text_scores_dev, const int64_t* text_rows_dev, int32_t kt,
+                        const float* img_scores_dev, const int64_t* img_rows_dev, int32_t ki, int32_t B,
+                        int32_t final_n, double tau, double* out_combined_dev, double* out_score_dev,
+                        int64_t* out_rows_dev, int8_t* out_modality_dev, uint8_t* out_low_conf_dev, void* stream) {
+  if (B <= 0) return fail(MMR_ERR_INVALID, "B must be >= 1");
+  if (kt < 0 || kt > FUSE_MAXK || ki < 0 || ki > FUSE_MAXK) return fail(MMR_ERR_INVALID, "kt, ki must be in [0, %d]", FUSE_MAXK);
+  if (final_n < 1) return fail(MMR_ERR_INVALID, "final_n must be >= 1");
+  if ((kt > 0 && (!text_scores_dev || !text_rows_dev)) || (ki > 0 && (!img_scores_dev || !img_rows_dev)))
+    return fail(MMR_ERR_INVALID, "NULL input buffer");
+  if (!out_combined_dev || !out_score_dev || !out_rows_dev || !out_modality_dev || !out_low_conf_dev)
+    return fail(MMR_ERR_INVALID, "NULL output buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int threads = 64;
+  fuse_kernel<<<(B + threads - 1) / threads, threads, 0, st>>>(
+      kt > 0 ? text_scores_dev : nullptr, kt > 0 ? text_rows_dev : nullptr, kt, ki > 0 ? img_scores_dev : nullptr,
+      ki > 0 ? img_rows_dev : nullptr, ki, B, final_n, tau, out_combined_dev, out_score_dev, out_rows_dev,
+      out_modality_dev, out_low_conf_dev);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return MMR_OK;
+}

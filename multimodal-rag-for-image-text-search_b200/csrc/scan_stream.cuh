@@ -1,0 +1,400 @@
+// K1 -- HBM-streaming exact scan for small query groups (1..4 queries sharing one row range).
+//
+// Replaces the Lance flat KNN behind LanceDBStore.search_text / search_image
+// (reference app/storage/lancedb_store.py:103-123): cos(q, x_n) for every row of the tenant's row
+// range, keep the best k under (score desc, row asc).
+//
+// Shape of the kernel (bandwidth-bound: algorithmic bytes = rows * D * sizeof(elem), read once):
+//   * persistent grid, one CTA per SM, NW consumer warps per CTA;
+//   * every warp owns a private ring of S stages in shared memory.  One stage = R consecutive index rows
+//     (R * D * sizeof(elem) contiguous bytes), filled by ONE 1-D bulk async copy (cp.async.bulk, the TMA
+//     engine without a descriptor) that signals an mbarrier.  NW * S stages (~192 KB/SM) are in flight,
+//     independent of register pressure;
+//   * chunk c of the row range goes to global warp (c mod total_warps): at any instant the chip reads
+//     one contiguous window of HBM;
+//   * per stage a warp computes R x NQ dot products: lane l holds 8/16-byte column slices of each row and
+//     the matching slice of every (normalised, fp32) query in registers; partial sums are combined with
+//     a transposing butterfly (V values -> V-1 shuffles, result spread one value per lane group);
+//   * scores never leave registers: a warp-resident sorted top-k list (topk.cuh) takes the rare score
+//     that beats the current k-th key;
+//   * warp lists -> CTA list (shared memory) -> per-CTA partial in global memory; the last CTA to finish
+//     (atomic ticket) merges all partials and writes the final [NQ, k] (score, row) -- one launch.
+#pragma once
+#include "common.cuh"
+#include "topk.cuh"
+
+namespace mmr {
+
+constexpr int K1_NW = 8;           // consumer warps per CTA
+constexpr int K1_THREADS = K1_NW * 32;
+constexpr int K1_SMEM_BUDGET = 200 * 1024;
+
+struct ScanItem {  // varlen mode: one contiguous row range of one query (rows are index-local ordinals)
+  uint32_t row_begin;
+  uint32_t row_end;
+  int32_t query;
+  int32_t pad;
+};
+
+struct StreamParams {
+  const void* rows;      // [n_rows, D] row-major, elem type E
+  const float* queries;  // [B, D] fp32, not necessarily unit norm (re-normalised here, lancedb_store.py:104)
+  int32_t q_first;       // first query of this group
+  int32_t nq;            // live queries in this group (1..NQ)
+  int32_t k;
+  uint32_t row_begin, row_end;  // uniform mode: the shared row range
+  uint64_t* partial;            // uniform: [grid, NQ, k]; varlen: [n_items, k]
+  unsigned int* ticket;         // zero on entry, left zero on exit
+  float* out_scores;            // [B, k]  (uniform mode only)
+  int64_t* out_rows;            // [B, k]
+  int64_t row_base;             // shard base added to the int64 row ids written out
+  const ScanItem* items;        // varlen mode (nullptr = uniform)
+  int32_t n_items;
+};
+
+template <typename E>
+struct ElemTraits;
+template <>
+struct ElemTraits<__nv_bfloat16> {
+  static constexpr int BYTES = 2;
+  // 32-bit word holds two bf16: low half = element 2i, high half = element 2i+1
+  static __device__ __forceinline__ void unpack(uint32_t w, float& a, float& b) {
+    a = __uint_as_float(w << 16);
+    b = __uint_as_float(w & 0xFFFF0000u);
+  }
+};
+template <>
+struct ElemTraits<__half> {
+  static constexpr int BYTES = 2;
+  static __device__ __forceinline__ void unpack(uint32_t w, float& a, float& b) {
+    const __half2 h = *reinterpret_cast<const __half2*>(&w);
+    const float2 f = __half22float2(h);
+    a = f.x;
+    b = f.y;
+  }
+};
+template <>
+struct ElemTraits<float> {
+  static constexpr int BYTES = 4;
+};
+
+// V partial sums per lane -> full sums, value i ending up (replicated) in lanes [i*32/V, (i+1)*32/V).
+// Each halving step exchanges half of the live values with the partner lane, so V values cost V-1
+// shuffles instead of 5V.
+template <int N, int OFF>
+__device__ __forceinline__ void transpose_reduce_step(float* v, int lane) {
+  if constexpr (OFF >= 1) {
+    if constexpr (N > 1) {
+      constexpr int H = N / 2;
+      const bool upper = (lane & OFF) != 0;
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        const float send = upper ? v[i] : v[i + H];
+        const float keep = upper ? v[i + H] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+      }
+      transpose_reduce_step<H, OFF / 2>(v, lane);
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], OFF);
+      transpose_reduce_step<1, OFF / 2>(v, lane);
+    }
+  }
+}
+template <int V>
+__device__ __forceinline__ float transpose_reduce(float (&v)[V], int lane) {
+  static_assert(V >= 1 && V <= 32 && (V & (V - 1)) == 0, "V must be a power of two <= 32");
+  transpose_reduce_step<V, 16>(v, lane);
+  return v[0];
+}
+
+template <typename E, int D, int NQ, int KPL>
+struct StreamCfg {
+  static constexpr int EB = ElemTraits<E>::BYTES;
+  static constexpr int ROW_BYTES = D * EB;
+  static constexpr int R = (EB == 2) ? 8 : 4;                        // rows per stage
+  static constexpr int V = R * NQ;                                   // dot products per stage per warp
+  static constexpr int STAGE_BYTES = R * ROW_BYTES;
+  static constexpr int S_RAW = K1_SMEM_BUDGET / (K1_NW * STAGE_BYTES);
+  static constexpr int S = S_RAW > 4 ? 4 : S_RAW;                    // stages per warp
+  static constexpr int VECB = (ROW_BYTES % 512 == 0) ? 16 : 8;       // bytes per lane per vector load
+  static constexpr int NV = ROW_BYTES / (32 * VECB);                 // vector loads per lane per row
+  static constexpr int RPV = VECB / 4;                               // 32-bit registers per vector
+  static constexpr int EPR = 4 / EB;                                 // elements per register
+  static constexpr int EPL = D / 32;                                 // elements per lane per row
+  static constexpr int KSLOTS = 32 * KPL;
+  static constexpr int RING_BYTES = K1_NW * S * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = RING_BYTES + K1_NW * S * 8 + 64;
+  static_assert(ROW_BYTES % (32 * 8) == 0, "D * sizeof(elem) must be a multiple of 256 bytes");
+  static_assert(S >= 2, "ring too shallow");
+  static_assert(V <= 32, "too many dot products per stage");
+  static_assert(K1_NW * NQ * KSLOTS * 8 <= RING_BYTES, "merge scratch must fit in the ring");
+};
+
+template <typename E, int D, int NQ, int KPL>
+__global__ void __launch_bounds__(K1_THREADS, 1) scan_stream_kernel(const StreamParams p) {
+  using C = StreamCfg<E, D, NQ, KPL>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::RING_BYTES);
+  __shared__ int s_last;
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int k = p.k;
+
+  // ---- this warp's ring ----
+  const uint32_t ring0 = smem_u32(smem) + uint32_t(warp) * (C::S * C::STAGE_BYTES);
+  const uint32_t bar0 = smem_u32(bars) + uint32_t(warp) * (C::S * 8);
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < C::S; ++s) mbar_init(bar0 + s * 8, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+
+  // ---- queries: normalise (f32, q / ||q||) and keep this lane's column slices in registers ----
+  float q[NQ][C::EPL];
+#pragma unroll
+  for (int qi = 0; qi < NQ; ++qi) {
+    const bool live = qi < p.nq;
+    const float* qsrc = p.queries + size_t(p.items ? 0 : (p.q_first + (live ? qi : 0))) * D;
+    float ss = 0.f;
+#pragma unroll
+    for (int t = 0; t < C::NV; ++t)
+#pragma unroll
+      for (int j = 0; j < C::RPV * C::EPR; ++j) {
+        const int e = (t * 32 + lane) * (C::RPV * C::EPR) + j;
+        const float x = (live && !p.items) ? qsrc[e] : 0.f;
+        q[qi][t * C::RPV * C::EPR + j] = x;
+        ss += x * x;
+      }
+    ss = warp_allreduce_sum(ss);
+    const float nrm = sqrtf(ss);
+    if (nrm > 0.f) {
+#pragma unroll
+      for (int e = 0; e < C::EPL; ++e) q[qi][e] = q[qi][e] / nrm;
+    }
+  }
+
+  WarpTopK<KPL> list[NQ];
+  uint64_t thr[NQ];
+#pragma unroll
+  for (int qi = 0; qi < NQ; ++qi) {
+    list[qi].clear();
+    thr[qi] = 0ull;
+  }
+
+  const int gwarp = blockIdx.x * K1_NW + warp;
+  const int twarps = gridDim.x * K1_NW;
+  const uint8_t* rows8 = reinterpret_cast<const uint8_t*>(p.rows);
+
+  int stage = 0;          // next ring stage this warp consumes (persists across row ranges)
+  uint32_t phase = 0;     // mbarrier parity of that stage
+
+  // One "job" = a row range scanned with chunk index c = first, first+stride, ...
+  auto scan_range = [&](uint32_t row_begin, uint32_t row_end, int first, int stride) {
+    const uint32_t nrows = row_end > row_begin ? row_end - row_begin : 0u;
+    const int nchunks = int((nrows + C::R - 1) / C::R);
+    auto issue = [&](int c, int s) {
+      // lane 0 only
+      const uint32_t r0 = row_begin + uint32_t(c) * C::R;
+      const uint32_t nr = min(uint32_t(C::R), row_end - r0);
+      const uint32_t bytes = nr * C::ROW_BYTES;
+      const uint32_t bar = bar0 + s * 8;
+      mbar_arrive_expect_tx(bar, bytes);
+      bulk_g2s(ring0 + s * C::STAGE_BYTES, rows8 + size_t(r0) * C::ROW_BYTES, bytes, bar);
+    };
+    // prologue: fill the ring
+    if (lane == 0) {
+      int sj = stage;
+#pragma unroll
+      for (int j = 0; j < C::S; ++j) {
+        const int c = first + j * stride;
+        if (c < nchunks) issue(c, sj);
+        sj = (sj + 1 == C::S) ? 0 : sj + 1;
+      }
+    }
+    for (int c = first; c < nchunks; c += stride) {
+      const int s = stage;
+      mbar_wait(bar0 + s * 8, phase);
+
+      const uint32_t base = ring0 + s * C::STAGE_BYTES + lane * C::VECB;
+      float acc[C::V];
+#pragma unroll
+      for (int i = 0; i < C::V; ++i) acc[i] = 0.f;
+#pragma unroll
+      for (int r = 0; r < C::R; ++r) {
+#pragma unroll
+        for (int t = 0; t < C::NV; ++t) {
+          uint32_t w[C::RPV];
+          const uint32_t addr = base + r * C::ROW_BYTES + t * (32 * C::VECB);
+          if constexpr (C::VECB == 16) {
+            lds_v4(addr, reinterpret_cast<uint32_t(&)[4]>(w));
+          } else {
+            lds_v2(addr, reinterpret_cast<uint32_t(&)[2]>(w));
+          }
+#pragma unroll
+          for (int j = 0; j < C::RPV; ++j) {
+            if constexpr (C::EB == 2) {
+              float a, b;
+              ElemTraits<E>::unpack(w[j], a, b);
+#pragma unroll
+              for (int qi = 0; qi < NQ; ++qi) {
+                acc[r * NQ + qi] = fmaf(a, q[qi][(t * C::RPV + j) * 2 + 0], acc[r * NQ + qi]);
+                acc[r * NQ + qi] = fmaf(b, q[qi][(t * C::RPV + j) * 2 + 1], acc[r * NQ + qi]);
+              }
+            } else {
+              const float a = __uint_as_float(w[j]);
+#pragma unroll
+              for (int qi = 0; qi < NQ; ++qi)
+                acc[r * NQ + qi] = fmaf(a, q[qi][t * C::RPV + j], acc[r * NQ + qi]);
+            }
+          }
+        }
+      }
+      // the stage has been read into registers: refill it (generic reads -> async-proxy write)
+      __syncwarp();
+      if (lane == 0) {
+        const int cn = c + C::S * stride;
+        if (cn < nchunks) {
+          fence_proxy_async();
+          issue(cn, s);
+        }
+      }
+
+      const float score = transpose_reduce<C::V>(acc, lane);
+      constexpr int LPV = 32 / C::V;  // lanes per value
+      const int vi = lane / LPV;      // value index = r * NQ + qi
+      const int r = vi / NQ;
+      const int myq = vi % NQ;
+      const uint32_t row = row_begin + uint32_t(c) * C::R + uint32_t(r);
+      const bool owner = (lane % LPV == 0) && row < row_end;
+      const uint64_t key = make_key(score, row);
+#pragma unroll
+      for (int qi = 0; qi < NQ; ++qi) {
+        if (qi < p.nq) thr[qi] = list[qi].offer(key, owner && myq == qi, thr[qi], k, lane);
+      }
+      if (++stage == C::S) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  };
+
+  if (p.items == nullptr) {
+    // ------------------------------ uniform mode ------------------------------
+    scan_range(p.row_begin, p.row_end, gwarp, twarps);
+
+    // warp lists -> shared memory (ring is idle now: every issued copy has been consumed)
+    __syncthreads();
+    uint64_t* wk = reinterpret_cast<uint64_t*>(smem);  // [NW][NQ][KSLOTS]
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) {
+#pragma unroll
+      for (int j = 0; j < KPL; ++j) wk[(warp * NQ + qi) * C::KSLOTS + j * 32 + lane] = list[qi].key[j];
+    }
+    __syncthreads();
+    // CTA-level merge: warp qi merges the NW lists of query qi and writes the CTA partial
+    if (warp < p.nq) {
+      const int qi = warp;
+      WarpTopK<KPL> m;
+      m.clear();
+      uint64_t t = 0ull;
+      for (int w = 0; w < K1_NW; ++w) t = m.merge_from(wk + (w * NQ + qi) * C::KSLOTS, k, 1, t, k, lane);
+      m.store(p.partial + (size_t(blockIdx.x) * NQ + qi) * k, k, lane);
+    }
+    // grid-level merge by the last CTA to arrive
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int prev = atomicAdd(p.ticket, 1u);
+      s_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int nparts = gridDim.x;
+    for (int qi = 0; qi < p.nq; ++qi) {
+      WarpTopK<KPL> m;
+      m.clear();
+      uint64_t t = 0ull;
+      for (int part = warp; part < nparts; part += K1_NW)
+        t = m.template merge_from<true>(p.partial + (size_t(part) * NQ + qi) * k, k, 1, t, k, lane);
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < KPL; ++j) wk[warp * C::KSLOTS + j * 32 + lane] = m.key[j];
+      __syncthreads();
+      if (warp == 0) {
+        WarpTopK<KPL> f;
+        f.clear();
+        uint64_t tf = 0ull;
+        for (int w = 0; w < K1_NW; ++w) tf = f.merge_from(wk + w * C::KSLOTS, k, 1, tf, k, lane);
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) {
+          const int pos = j * 32 + lane;
+          if (pos < k) {
+            const uint64_t key = f.key[j];
+            const size_t o = size_t(p.q_first + qi) * k + pos;
+            p.out_scores[o] = key ? key_score(key) : -INFINITY;
+            p.out_rows[o] = key ? int64_t(key_row(key)) + p.row_base : int64_t(-1);
+          }
+        }
+      }
+    }
+    if (threadIdx.x == 0) *p.ticket = 0u;  // ready for the next launch
+  } else {
+    // ------------------------------ varlen mode (NQ == 1) ------------------------------
+    // item i -> global warp (i mod total_warps); each item is one (query, row range); the partial of
+    // every item is merged per query by merge_items_kernel.
+    for (int it = gwarp; it < p.n_items; it += twarps) {
+      const ScanItem item = p.items[it];
+      // load + normalise this item's query
+      const float* qsrc = p.queries + size_t(item.query) * D;
+      float ss = 0.f;
+#pragma unroll
+      for (int t = 0; t < C::NV; ++t)
+#pragma unroll
+        for (int j = 0; j < C::RPV * C::EPR; ++j) {
+          const float x = qsrc[(t * 32 + lane) * (C::RPV * C::EPR) + j];
+          q[0][t * C::RPV * C::EPR + j] = x;
+          ss += x * x;
+        }
+      ss = warp_allreduce_sum(ss);
+      const float nrm = sqrtf(ss);
+      if (nrm > 0.f) {
+#pragma unroll
+        for (int e = 0; e < C::EPL; ++e) q[0][e] = q[0][e] / nrm;
+      }
+      list[0].clear();
+      thr[0] = 0ull;
+      scan_range(item.row_begin, item.row_end, 0, 1);
+      list[0].store(p.partial + size_t(it) * k, k, lane);
+    }
+  }
+}
+
+// Varlen tail: one warp per query merges the partial lists of that query's items
+// (items of a query are contiguous: [item_off[q], item_off[q+1])).
+template <int KPL>
+__global__ void merge_items_kernel(const uint64_t* __restrict__ partial, const int32_t* __restrict__ item_off, int nq,
+                                   int k, float* __restrict__ out_scores, int64_t* __restrict__ out_rows,
+                                   int64_t row_base) {
+  const int lane = threadIdx.x & 31;
+  const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (qi >= nq) return;
+  WarpTopK<KPL> m;
+  m.clear();
+  uint64_t t = 0ull;
+  const int i0 = item_off[qi], i1 = item_off[qi + 1];
+  t = m.template merge_from<true>(partial + size_t(i0) * k, (i1 - i0) * k, 1, t, k, lane);
+#pragma unroll
+  for (int j = 0; j < KPL; ++j) {
+    const int pos = j * 32 + lane;
+    if (pos < k) {
+      const uint64_t key = m.key[j];
+      out_scores[size_t(qi) * k + pos] = key ? key_score(key) : -INFINITY;
+      out_rows[size_t(qi) * k + pos] = key ? int64_t(key_row(key)) + row_base : int64_t(-1);
+    }
+  }
+}
+
+}  // namespace mmr

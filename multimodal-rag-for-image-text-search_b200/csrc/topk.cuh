@@ -1,0 +1,87 @@
+// Warp-resident exact top-k: a descending-sorted list of u64 keys spread over the 32 lanes of a warp
+// (KPL keys per lane -> capacity 32*KPL), maintained with shuffles only.  Inserts are rare once the
+// threshold (the k-th key) has warmed up, so the scan's common path is one compare per score.
+#pragma once
+#include "common.cuh"
+
+namespace mmr {
+
+template <int KPL>
+struct WarpTopK {
+  // position p (0 = best) lives in lane p % 32, slot p / 32
+  uint64_t key[KPL];
+
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) key[j] = 0ull;
+  }
+
+  // k-th best key (threshold); k in [1, 32*KPL].  Uniform across the warp.
+  __device__ __forceinline__ uint64_t kth(int k) const {
+    const int p = k - 1;
+    uint64_t v = key[0];
+#pragma unroll
+    for (int j = 1; j < KPL; ++j)
+      if ((p >> 5) == j) v = key[j];
+    return shfl_u64(v, p & 31);
+  }
+
+  // Insert a warp-uniform candidate `c` (distinct from every key already held).  Keys ranking below
+  // it shift down one position; the last one falls off the end.
+  __device__ __forceinline__ void insert(uint64_t c, int lane) {
+    uint64_t carry = ~0ull;  // "element before position 0": never outranked by c
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+      const uint64_t mine = key[j];
+      uint64_t up = shfl_up_u64(mine, 1);
+      if (lane == 0) up = carry;
+      carry = shfl_u64(mine, 31);
+      key[j] = (c > mine) ? ((c > up) ? up : c) : mine;
+    }
+  }
+
+  // Offer up to 32 candidates (one per lane, `valid` lanes only) against threshold `thr`; returns the
+  // updated threshold.  All lanes must call.
+  __device__ __forceinline__ uint64_t offer(uint64_t cand, bool valid, uint64_t thr, int k, int lane) {
+    unsigned m = __ballot_sync(0xffffffffu, valid && cand > thr);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const uint64_t c = shfl_u64(cand, src);
+      if (c > thr) {
+        insert(c, lane);
+        thr = kth(k);
+      }
+    }
+    return thr;
+  }
+
+  // Merge `count` keys from memory, element i at base[i * stride].  GLOBAL = true reads through L2
+  // only (ld.global.cg): the keys were written by other CTAs of the same launch.
+  template <bool GLOBAL = false>
+  __device__ __forceinline__ uint64_t merge_from(const uint64_t* base, int count, int stride, uint64_t thr, int k,
+                                                 int lane) {
+    for (int i0 = 0; i0 < count; i0 += 32) {
+      const int i = i0 + lane;
+      const bool valid = i < count;
+      uint64_t c = 0ull;
+      if (valid) {
+        if constexpr (GLOBAL) c = __ldcg(reinterpret_cast<const unsigned long long*>(base) + size_t(i) * stride);
+        else c = base[size_t(i) * stride];
+      }
+      thr = offer(c, valid && c != 0ull, thr, k, lane);
+    }
+    return thr;
+  }
+
+  // Write the first k positions to dst[0..k).
+  __device__ __forceinline__ void store(uint64_t* dst, int k, int lane) const {
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+      const int p = j * 32 + lane;
+      if (p < k) dst[p] = key[j];
+    }
+  }
+};
+
+}  // namespace mmr

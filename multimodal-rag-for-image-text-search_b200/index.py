@@ -1,0 +1,177 @@
+"""ResidentIndex -- one HBM-resident row matrix (bf16/fp16/fp32) + tenant segments, searched through the
+C ABI.  PyTorch is only the plumbing here: it owns the device memory and the stream.
+
+Reference anchors: the matrix is the `embedding` column of one LanceDB collection
+(app/storage/lancedb_store.py:33-44), the segments are the `user_id == '...'` predicate (:107,118,141-144),
+`search` is the scan + top-k of search_text / search_image (:103-123).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+_DTYPES = {
+    "bf16": (N.MMR_BF16, torch.bfloat16),
+    "f16": (N.MMR_F16, torch.float16),
+    "f32": (N.MMR_F32, torch.float32),
+}
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class ResidentIndex:
+    """Rows live in `self.rows` ([n, dim] on `device`); `seg_offsets` ([T+1]) delimit tenants."""
+
+    def __init__(self, rows: torch.Tensor, seg_offsets: Optional[Sequence[int]] = None, row_base: int = 0):
+        if not rows.is_cuda:
+            raise N.NativeError("ResidentIndex needs CUDA rows: this package has no CPU path")
+        if rows.dim() != 2 or not rows.is_contiguous():
+            raise ValueError("rows must be a contiguous [n, dim] tensor")
+        kinds = {v[1]: (k, v[0]) for k, v in _DTYPES.items()}
+        if rows.dtype not in kinds:
+            raise ValueError(f"unsupported row dtype {rows.dtype}")
+        self.dtype_name, self._dtype_code = kinds[rows.dtype]
+        self.rows = rows
+        self.device = rows.device
+        self.n_rows, self.dim = int(rows.shape[0]), int(rows.shape[1])
+        self.row_base = int(row_base)
+        self.seg_offsets = None if seg_offsets is None else np.ascontiguousarray(seg_offsets, dtype=np.int64)
+        self._handle = C.c_void_p()
+        self._ws: Optional[torch.Tensor] = None
+        self._ws_key = (0, 0)
+        lib = N.lib()
+        nseg = 0 if self.seg_offsets is None else len(self.seg_offsets) - 1
+        segp = None if self.seg_offsets is None else self.seg_offsets.ctypes.data
+        N.check(lib.mmr_index_create(self.device.index or 0, self.dim, self._dtype_code, self.n_rows,
+                                     rows.data_ptr() if self.n_rows else None, segp, nseg, self.row_base,
+                                     C.byref(self._handle)))
+
+    # -- construction helpers -------------------------------------------------------------------
+    @classmethod
+    def from_f32(cls, rows_f32, seg_offsets=None, dtype: str = "bf16", device="cuda:0", normalize: bool = False,
+                 row_base: int = 0) -> "ResidentIndex":
+        """L1 loader: fp32 rows (host numpy / host or device torch) -> resident rows of `dtype`."""
+        code, tdt = _DTYPES[dtype]
+        device = torch.device(device)
+        lib = N.lib()
+        if isinstance(rows_f32, np.ndarray):
+            src = np.ascontiguousarray(rows_f32, dtype=np.float32)
+            n, d = src.shape
+            dst = torch.empty((n, d), dtype=tdt, device=device)
+            with torch.cuda.device(device):
+                N.check(lib.mmr_load_rows_f32_host(device.index or 0, src.ctypes.data, _ptr(dst) if n else None, code,
+                                                   n, d, int(normalize), _stream_ptr(device)))
+        else:
+            src = rows_f32.to(device=device, dtype=torch.float32).contiguous()
+            n, d = src.shape
+            dst = torch.empty((n, d), dtype=tdt, device=device)
+            with torch.cuda.device(device):
+                N.check(lib.mmr_convert_rows_f32(_ptr(src) if n else None, _ptr(dst) if n else None, code, n, d,
+                                                 int(normalize), _stream_ptr(device)))
+        return cls(dst, seg_offsets, row_base)
+
+    def close(self) -> None:
+        if self._handle:
+            N.lib().mmr_index_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- search ---------------------------------------------------------------------------------
+    def _workspace(self, b: int, k: int) -> torch.Tensor:
+        need = N.lib().mmr_search_workspace_bytes(self._handle, b, k)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.zeros(int(need), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def search(self, queries: torch.Tensor, k: int, segments: Optional[Sequence[int]] = None,
+               out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Device-resident search: queries [B, dim] f32 on the index device -> (scores [B,k] f32, rows [B,k] i64)."""
+        if queries.dim() == 1:
+            queries = queries[None, :]
+        if not queries.is_cuda or queries.dtype != torch.float32 or not queries.is_contiguous():
+            raise ValueError("queries must be a contiguous float32 CUDA tensor")
+        if queries.shape[1] != self.dim:
+            raise ValueError(f"query dim {queries.shape[1]} != index dim {self.dim}")
+        b = int(queries.shape[0])
+        k = max(int(k), 1)
+        if out is None:
+            scores = torch.empty((b, k), dtype=torch.float32, device=self.device)
+            rows = torch.empty((b, k), dtype=torch.int64, device=self.device)
+        else:
+            scores, rows = out
+        seg_arr = None
+        if segments is not None:
+            seg_arr = np.ascontiguousarray(segments, dtype=np.int32)
+            if seg_arr.shape != (b,):
+                raise ValueError("segments must have one entry per query")
+        ws = self._workspace(b, k)
+        with torch.cuda.device(self.device):
+            N.check(N.lib().mmr_search(self._handle, queries.data_ptr(), None if seg_arr is None else seg_arr.ctypes.data,
+                                       b, k, scores.data_ptr(), rows.data_ptr(), ws.data_ptr(), ws.numel(),
+                                       _stream_ptr(self.device)))
+        return scores, rows
+
+    def search_host(self, queries: np.ndarray, k: int, segments: Optional[Sequence[int]] = None):
+        """Host-buffer search (H2D + scan + D2H + sync inside the C call) -> numpy (scores, rows)."""
+        q = np.ascontiguousarray(np.atleast_2d(queries), dtype=np.float32)
+        if q.shape[1] != self.dim:
+            raise ValueError(f"query dim {q.shape[1]} != index dim {self.dim}")
+        b = q.shape[0]
+        k = max(int(k), 1)
+        scores = np.empty((b, k), dtype=np.float32)
+        rows = np.empty((b, k), dtype=np.int64)
+        seg_arr = None if segments is None else np.ascontiguousarray(segments, dtype=np.int32)
+        with torch.cuda.device(self.device):
+            N.check(N.lib().mmr_search_host(self._handle, q.ctypes.data, None if seg_arr is None else seg_arr.ctypes.data,
+                                            b, k, scores.ctypes.data, rows.ctypes.data, _stream_ptr(self.device)))
+        return scores, rows
+
+
+def merge_topk(scores: torch.Tensor, rows: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K4: [G, B, k] shard-local results -> [B, k]."""
+    g, b, k = scores.shape
+    out_s = torch.empty((b, k), dtype=torch.float32, device=scores.device)
+    out_r = torch.empty((b, k), dtype=torch.int64, device=scores.device)
+    with torch.cuda.device(scores.device):
+        N.check(N.lib().mmr_merge_topk(scores.contiguous().data_ptr(), rows.contiguous().data_ptr(), g, b, k,
+                                       out_s.data_ptr(), out_r.data_ptr(), _stream_ptr(scores.device)))
+    return out_s, out_r
+
+
+def fuse(text: Optional[Tuple[torch.Tensor, torch.Tensor]], image: Optional[Tuple[torch.Tensor, torch.Tensor]],
+         final_n: int, tau: float):
+    """K5: device fusion + gate for the rerank-off path.  Returns dict of device tensors."""
+    ref = text if text is not None else image
+    if ref is None:
+        raise ValueError("need at least one modality")
+    dev = ref[0].device
+    b = int(ref[0].shape[0])
+    kt = 0 if text is None else int(text[0].shape[1])
+    ki = 0 if image is None else int(image[0].shape[1])
+    comb = torch.empty((b, final_n), dtype=torch.float64, device=dev)
+    score = torch.empty((b, final_n), dtype=torch.float64, device=dev)
+    rows = torch.empty((b, final_n), dtype=torch.int64, device=dev)
+    mod = torch.empty((b, final_n), dtype=torch.int8, device=dev)
+    low = torch.empty((b,), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().mmr_fuse(_ptr(text[0].contiguous()) if kt else None, _ptr(text[1].contiguous()) if kt else None, kt,
+                                 _ptr(image[0].contiguous()) if ki else None, _ptr(image[1].contiguous()) if ki else None, ki,
+                                 b, int(final_n), float(tau), comb.data_ptr(), score.data_ptr(), rows.data_ptr(),
+                                 mod.data_ptr(), low.data_ptr(), _stream_ptr(dev)))
+    return {"combined": comb, "score": score, "rows": rows, "modality": mod, "low_conf": low}

@@ -1,0 +1,169 @@
+"""K5 fusion/gate bit-exactness, and the B200Store / retrieve() drop-in against the oracle store."""
+import copy
+import importlib
+import json
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import flat_search as ofs
+from oracle import fusion as ofu
+from tests import util
+
+pytestmark = pytest.mark.gpu
+PKG = "multimodal-rag-for-image-text-search_b200"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def mmr():
+    pkg = importlib.import_module(PKG)
+    pkg._native.lib()
+    return pkg
+
+
+def _oracle_fuse(cos_t, cos_i, final_n, tau):
+    """What search_* -> _fuse_results -> _confidence_low give for f32 cosine scores (rerank off)."""
+    one = np.float32(1.0)
+    text = [{"id": ("t", j), "score": 1.0 - float(one - c)} for j, c in enumerate(cos_t)]
+    img = [{"id": ("i", j), "score": 1.0 - float(one - c)} for j, c in enumerate(cos_i)]
+    fused = ofu.fuse_results(text, img, final_n)
+    return fused, ofu.confidence_low(fused, tau)
+
+
+@pytest.mark.parametrize("kt,ki", [(50, 12), (10, 10), (1, 1), (7, 0), (0, 12), (64, 64), (8, 3)])
+def test_fuse_kernel_bit_exact(mmr, kt, ki):
+    rng = np.random.default_rng(kt * 100 + ki)
+    b = 33
+    ts = np.sort(rng.uniform(-0.1, 0.9, size=(b, max(kt, 1))).astype(np.float32), axis=1)[:, ::-1].copy()
+    is_ = np.sort(rng.uniform(0.1, 0.4, size=(b, max(ki, 1))).astype(np.float32), axis=1)[:, ::-1].copy()
+    ts[1] = 0.5                                   # std == 0 -> all z == 0 -> stable order decides
+    tr = np.tile(np.arange(max(kt, 1), dtype=np.int64), (b, 1)) + 1000
+    ir = np.tile(np.arange(max(ki, 1), dtype=np.int64), (b, 1)) + 5000
+    nt = rng.integers(0, kt + 1, size=b) if kt else np.zeros(b, int)
+    ni = rng.integers(0, ki + 1, size=b) if ki else np.zeros(b, int)
+    nt[0], ni[0] = 0, 0                           # no hits at all -> low confidence
+    for j in range(b):
+        tr[j, nt[j]:] = -1
+        ir[j, ni[j]:] = -1
+    dev = "cuda"
+    text = (torch.from_numpy(ts[:, :kt].copy()).to(dev), torch.from_numpy(tr[:, :kt].copy()).to(dev)) if kt else None
+    img = (torch.from_numpy(is_[:, :ki].copy()).to(dev), torch.from_numpy(ir[:, :ki].copy()).to(dev)) if ki else None
+    for final_n, tau in ((4, 0.25), (1, 0.0), (10, 0.9)):
+        out = {k: v.cpu().numpy() for k, v in mmr.fuse(text, img, final_n, tau).items()}
+        for j in range(b):
+            fused, low = _oracle_fuse(ts[j, :nt[j]], is_[j, :ni[j]], final_n, tau)
+            assert bool(out["low_conf"][j]) is low, (j, final_n, tau)
+            for o in range(final_n):
+                if o < len(fused):
+                    kind, pos = fused[o]["id"]
+                    assert out["modality"][j, o] == (0 if kind == "t" else 1)
+                    assert out["rows"][j, o] == (tr[j, pos] if kind == "t" else ir[j, pos])
+                    assert out["combined"][j, o] == fused[o]["combined_score"], (j, o)   # bit-exact float64
+                    assert out["score"][j, o] == fused[o]["score"]
+                else:
+                    assert out["rows"][j, o] == -1 and out["modality"][j, o] == -1
+
+
+def _rows(n, dim, seed, users, prefix):
+    rng = np.random.default_rng(seed)
+    emb = rng.standard_normal((n, dim)).astype(np.float32) * 2
+    return [SimpleNamespace(chunk_id=f"{prefix}{i}", user_id=users[i % len(users)], document_id=f"d{i % 5}",
+                            modality="text" if prefix == "t" else "image", embedding=emb[i].tolist(),
+                            meta={"i": i}) for i in range(n)]
+
+
+def test_store_matches_oracle_store(mmr):
+    """search_text / search_image through B200Store vs the oracle's LanceDBStore restatement: same chunk ids
+    (tolerance-aware), scores within 1e-3, same dict shape; upsert = delete + add; unknown tenant -> []."""
+    users = ["alice", "bob", "o'brien"]
+    trows, irows = _rows(3000, 384, 1, users, "t"), _rows(800, 512, 2, users, "i")
+    gpu, cpu = mmr.B200Store(), ofs.OracleStore()
+    for st in (gpu, cpu):
+        st.upsert_text_vectors([mmr.VectorRow(**r.__dict__) for r in trows] if st is gpu else trows)
+        st.upsert_image_vectors([mmr.VectorRow(**r.__dict__) for r in irows] if st is gpu else irows)
+    moved = copy.deepcopy(trows[10])
+    moved.embedding = trows[11].embedding          # re-upsert an existing chunk with a new vector
+    gpu.upsert_text_vectors([mmr.VectorRow(**moved.__dict__)])
+    cpu.upsert_text_vectors([moved])
+    assert gpu.get_index_version("alice") >= 2 and gpu.get_index_version("nobody") == 0
+    rng = np.random.default_rng(3)
+    for user in users + ["nobody"]:
+        for fn, dim, k in (("search_text", 384, 50), ("search_image", 512, 12), ("search_text", 384, 0)):
+            q = rng.standard_normal(dim).astype(np.float32)
+            got = getattr(gpu, fn)(user, q.tolist(), k)
+            want = getattr(cpu, fn)(user, q.tolist(), k)
+            assert len(got) == len(want)
+            if not want:
+                assert got == []
+                continue
+            assert set(got[0]) == {"chunk_id", "score", "meta"} and isinstance(got[0]["score"], float)
+            wscore = {w["chunk_id"]: w["score"] for w in want}
+            kth = want[-1]["score"]
+            for g in got:
+                if g["chunk_id"] in wscore:
+                    assert abs(g["score"] - wscore[g["chunk_id"]]) <= util.TOL_BF16
+                else:
+                    assert g["score"] >= kth - 2 * util.TOL_BF16     # only boundary swaps inside the tolerance
+                assert g["meta"] == {"i": int(g["chunk_id"][1:])}
+            clear = [w["chunk_id"] for w in want if w["score"] > kth + 2 * util.TOL_BF16]
+            assert set(clear) <= {g["chunk_id"] for g in got}
+            assert [g["score"] for g in got] == sorted((g["score"] for g in got), reverse=True)
+    # the re-upserted chunk now sits next to its twin
+    hits = gpu.search_text(moved.user_id, moved.embedding, 5)
+    assert {h["chunk_id"] for h in hits[:2]} == {"t10", "t11"} or hits[0]["chunk_id"] == "t10"
+    # batched entry point == single calls
+    qs = rng.standard_normal((5, 384)).astype(np.float32)
+    us = ["alice", "bob", "nobody", "alice", "o'brien"]
+    batch = gpu.search_text_batch(us, qs, 10)
+    for u, q, b in zip(us, qs, batch):
+        assert b == gpu.search_text(u, q.tolist(), 10)
+
+
+def test_arrow_load_and_retrieve_end_to_end(mmr):
+    """Reference schema in (Arrow), retrieve()/retrieve_text()/retrieve_images() out, fused like the oracle."""
+    retrieve = importlib.import_module(PKG + ".retrieve")
+    cache = importlib.import_module(PKG + ".cache")
+    settings_mod = importlib.import_module(PKG + ".settings")
+    cache.clear_all_caches()
+    n_t, n_i = 4000, 1500
+    temb, iemb = util.unit_rows(n_t, 384, 5), util.unit_rows(n_i, 512, 6)
+    users_t = [f"u{i % 3}" for i in range(n_t)]
+    users_i = [f"u{i % 3}" for i in range(n_i)]
+    store = mmr.B200Store()
+    store.load_arrow("text_collection", mmr.make_arrow_table([f"t{i}" for i in range(n_t)], users_t, ["d"] * n_t,
+                                                             ["text"] * n_t, temb, [json.dumps({"i": i}) for i in range(n_t)]))
+    store.load_arrow("image_collection", mmr.make_arrow_table([f"i{i}" for i in range(n_i)], users_i, ["d"] * n_i,
+                                                              ["image"] * n_i, iemb, [None] * n_i))
+    chunks = {f"t{i}": SimpleNamespace(id=f"t{i}", document_id="d", modality="text", text=f"text {i}", meta={},
+                                       page_no=i, start_ts=None, end_ts=None, file_path=None) for i in range(n_t)}
+    chunks.update({f"i{i}": SimpleNamespace(id=f"i{i}", document_id="d", modality="image", text=None, meta={},
+                                            page_no=None, start_ts=None, end_ts=None, file_path=f"/f/{i}.jpg") for i in range(n_i)})
+    qt, qi = util.queries(1, 384, seed=9)[0], util.queries(1, 512, seed=10)[0]
+    retrieve.configure(store=store, metadata=SimpleNamespace(get_chunk=chunks.get),
+                       text_encoder=lambda texts: qt[None, :], image_query_encoder=lambda q: qi,
+                       retrieval_settings=settings_mod.RetrievalSettings(use_rerank=False))
+    fused = retrieve.retrieve("u1", "what is in the picture?")
+    # oracle: same tenant rows, fp32
+    sel_t = np.array([i for i in range(n_t) if i % 3 == 1]); sel_i = np.array([i for i in range(n_i) if i % 3 == 1])
+    dt, it = ofs.flat_search(temb[sel_t], qt, 50); di, ii = ofs.flat_search(iemb[sel_i], qi, 12)
+    text = [{"chunk_id": f"t{sel_t[j]}", "score": 1.0 - float(d)} for d, j in zip(dt, it)]
+    img = [{"chunk_id": f"i{sel_i[j]}", "score": 1.0 - float(d)} for d, j in zip(di, ii)]
+    want = ofu.fuse_results(text, img, 4)
+    assert len(fused) == 4 and all("combined_score" in f and "metadata" in f for f in fused)
+    assert [f["chunk_id"] for f in fused[:2]] == [w["chunk_id"] for w in want[:2]]
+    for f, w in zip(fused, want):
+        assert abs(f["combined_score"] - w["combined_score"]) < 0.05   # z-scores amplify the 1e-3 score tolerance
+    assert retrieve._confidence_low(fused) is ofu.confidence_low(want, 0.25)
+    assert retrieve.retrieve("u1", "what is in the picture?") is fused              # cache hit, same version
+    assert retrieve.retrieve("nobody", "x") == []
+    # device fusion of the same request agrees with the host fusion bit for bit
+    ts, tr = store._text_table.resident().search(torch.from_numpy(qt[None]).cuda(), 50, [store._text_table._seg_of["u1"]])
+    is_, ir = store._image_table.resident().search(torch.from_numpy(qi[None]).cuda(), 12, [store._image_table._seg_of["u1"]])
+    out = mmr.fuse((ts, tr), (is_, ir), 4, 0.25)
+    assert out["combined"][0].cpu().tolist() == [f["combined_score"] for f in fused]
+    assert bool(out["low_conf"][0]) is retrieve._confidence_low(fused)
+    cache.clear_all_caches()
