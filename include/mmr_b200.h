@@ -121,6 +121,15 @@ int mmr_fuse(const float* text_scores_dev, const int64_t* text_rows_dev, int32_t
              double* out_combined_dev, double* out_score_dev, int64_t* out_rows_dev, int8_t* out_modality_dev,
              uint8_t* out_low_conf_dev, void* stream);
 
+/*
+ * Validation hook for the tensor-core path (K2): raw cosine scores of B queries against rows
+ * [row_begin, row_end) as computed by the tcgen05 contraction (bf16 queries x bf16 rows, fp32 accumulate),
+ * written to out_scores_dev[b * out_ld + (row - row_begin)].  workspace as for mmr_search(B, k = 10).
+ */
+int mmr_debug_umma_scores(const mmr_index* index, const float* queries_dev, int32_t B, int64_t row_begin,
+                          int64_t row_end, float* out_scores_dev, int64_t out_ld, void* workspace_dev,
+                          size_t workspace_bytes, void* stream);
+
 /* Introspection used by bench.py / tests: launches issued by this library since load, device facts. */
 int64_t mmr_launch_count(void);
 int mmr_device_sm_count(int device, int* out_sms);

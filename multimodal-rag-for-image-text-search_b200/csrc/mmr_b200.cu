@@ -61,7 +61,7 @@ struct mmr_index {
   size_t ws_bytes = 0;
   int cap_b = 0, cap_k = 0;
 #ifdef MMR_WITH_UMMA
-  UmmaIndexState umma;
+  mutable UmmaIndexState umma;
 #endif
 };
 
@@ -477,6 +477,29 @@ extern "C" int mmr_search_host(mmr_index* ix, const float* queries_host, const i
   memcpy(out_rows_host, ix->h_rows, size_t(B) * k * 8);
   return MMR_OK;
 }
+
+#ifdef MMR_WITH_UMMA
+// Debug / validation hook: raw K2 scores (tensor-core contraction only, no top-k) for rows [row_begin, row_end).
+extern "C" int mmr_debug_umma_scores(const mmr_index* ix, const float* queries_dev, int32_t B, int64_t row_begin,
+                                     int64_t row_end, float* out_scores_dev, int64_t out_ld, void* workspace_dev,
+                                     size_t workspace_bytes, void* stream) {
+  if (!ix || !queries_dev || !out_scores_dev || !workspace_dev) return fail(MMR_ERR_INVALID, "NULL argument");
+  if (ix->dtype != MMR_BF16) return fail(MMR_ERR_UNSUPPORTED, "K2 needs bf16 rows");
+  if (B <= 0 || row_begin < 0 || row_end > ix->n_rows || row_end <= row_begin || out_ld < row_end - row_begin)
+    return fail(MMR_ERR_INVALID, "bad range");
+  if (workspace_bytes < umma_workspace_bytes(ix->sm_count, ix->dim, B, 10)) return fail(MMR_ERR_WORKSPACE, "workspace too small");
+  int rc = umma_search(ix->umma, ix->rows, ix->n_rows, ix->dim, ix->sm_count, queries_dev, B, 10, uint32_t(row_begin),
+                       uint32_t(row_end), 0, nullptr, nullptr, static_cast<uint8_t*>(workspace_dev),
+                       static_cast<cudaStream_t>(stream), g_err, out_scores_dev, out_ld);
+  if (rc == MMR_OK) g_launches += 2;
+  return rc;
+}
+#else
+extern "C" int mmr_debug_umma_scores(const mmr_index*, const float*, int32_t, int64_t, int64_t, float*, int64_t, void*,
+                                     size_t, void*) {
+  return fail(MMR_ERR_UNSUPPORTED, "built without the tcgen05 kernel");
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------ K4 / K5
 extern "C" int mmr_merge_topk(const float* scores_dev, const int64_t* rows_dev, int32_t G, int32_t B, int32_t k,

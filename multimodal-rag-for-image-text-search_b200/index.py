@@ -127,6 +127,18 @@ class ResidentIndex:
                                        _stream_ptr(self.device)))
         return scores, rows
 
+    def debug_umma_scores(self, queries: torch.Tensor, row_begin: int, row_end: int) -> torch.Tensor:
+        """Validation hook: raw tensor-core (K2) scores [B, row_end-row_begin] without the top-k epilogue."""
+        b = int(queries.shape[0])
+        n = int(row_end - row_begin)
+        out = torch.full((b, n), float("nan"), dtype=torch.float32, device=self.device)
+        ws = self._workspace(max(b, 8), 10)
+        with torch.cuda.device(self.device):
+            N.check(N.lib().mmr_debug_umma_scores(self._handle, queries.contiguous().data_ptr(), b, int(row_begin),
+                                                  int(row_end), out.data_ptr(), n, ws.data_ptr(), ws.numel(),
+                                                  _stream_ptr(self.device)))
+        return out
+
     def search_host(self, queries: np.ndarray, k: int, segments: Optional[Sequence[int]] = None):
         """Host-buffer search (H2D + scan + D2H + sync inside the C call) -> numpy (scores, rows)."""
         q = np.ascontiguousarray(np.atleast_2d(queries), dtype=np.float32)
