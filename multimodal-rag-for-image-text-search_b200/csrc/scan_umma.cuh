@@ -249,7 +249,7 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int col = c * 32 + j;
-            if (col < nvalid) p.dump[qrow * p.dump_ld + int64_t(row0 - p.row_begin) + col] = __uint_as_float(v[j]);
+            if (col < nvalid && qt * K2_BM + ql < p.B) p.dump[qrow * p.dump_ld + int64_t(row0 - p.row_begin) + col] = __uint_as_float(v[j]);
           }
         } else {
           if (nvalid < K2_NT) {
