@@ -22,6 +22,7 @@
 #pragma once
 #include <cuda.h>
 
+#include <cstdlib>
 #include <string>
 
 #include "common.cuh"
@@ -34,7 +35,7 @@ constexpr int K2_BM = 128;               // queries per tile  (UMMA M, TMEM lane
 constexpr int K2_NT = 128;               // index rows per tile (UMMA N, TMEM columns per accumulator)
 constexpr int K2_SLICE = 128 * 128;      // bytes of one [128 rows x 64 bf16] SWIZZLE_128B box
 constexpr int K2_ACC = 4;                // TMEM accumulators (4 x 128 = 512 columns)
-constexpr int K2_MAX_STAGES = 6;
+constexpr int K2_MAX_STAGES = 13;
 constexpr int K2_SMEM_LIMIT = 227 * 1024;
 
 struct UmmaParams {
@@ -45,7 +46,8 @@ struct UmmaParams {
   uint32_t row_begin, row_end;
   int32_t n_qtiles, n_rslots;
   uint64_t* partial;  // [n_qtiles * n_rslots][128][k]
-  float* dump;        // DUMP mode: raw scores [n_qtiles*128][dump_ld]
+  const void* qbf16;  // TS mode: normalised bf16 queries of this launch, [B][D]
+  float* dump;        // DUMP mode: raw scores [B][dump_ld]
   int64_t dump_ld;
 };
 
@@ -124,18 +126,49 @@ __device__ __noinline__ uint64_t k2_list_insert(uint64_t* mine, int k, uint64_t 
   return mine[size_t(k - 1) * K2_BM];
 }
 
-template <bool DUMP>
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :
+      : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// TS = true : the query tile is the A operand *in tensor memory* (128 lanes x D/2 packed-bf16 columns, written once
+//             by the epilogue threads with tcgen05.st); shared memory holds only the index ring (up to 13 x 16 KB
+//             in flight) and the tensor pipe reads half as many shared-memory bytes per MMA.  2 accumulators.
+// TS = false: the query tile is a shared-memory operand (TMA, SWIZZLE_128B), 4 accumulators.
+template <bool DUMP, bool TS>
 __global__ void __launch_bounds__(K2_THREADS, 1)
 scan_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x,
                  const UmmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int NACC = TS ? 2 : K2_ACC;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int ks = p.ks, nstages = p.nstages, k = p.k;
+  const int qslices = TS ? 0 : ks;                     // shared-memory slices taken by the query tile
+  const uint32_t acc_col0 = TS ? uint32_t(ks * 32) : 0u;  // TS: columns [0, D/2) hold the packed query tile
 
   const uint32_t q_s = smem_u32(smem);
-  const uint32_t st_s = q_s + uint32_t(ks) * K2_SLICE;
-  uint64_t* lists = reinterpret_cast<uint64_t*>(smem + size_t(ks + nstages) * K2_SLICE);  // [k][128]
+  const uint32_t st_s = q_s + uint32_t(qslices) * K2_SLICE;
+  uint64_t* lists = reinterpret_cast<uint64_t*>(smem + size_t(qslices + nstages) * K2_SLICE);  // [k][128]
   uint64_t* bars = lists + size_t(k) * K2_BM;
   const uint32_t bar_full = smem_u32(bars);                      // [K2_MAX_STAGES]
   const uint32_t bar_empty = bar_full + K2_MAX_STAGES * 8;       // [K2_MAX_STAGES]
@@ -159,9 +192,9 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       mbar_init(bar_tfull + a * 8, 1);
       mbar_init(bar_tempty + a * 8, 4);  // one arrival per epilogue warp
     }
-    mbar_init(bar_q, 1);
+    mbar_init(bar_q, TS ? 4 : 1);
     fence_mbar_init();
-    tma_prefetch_desc(&tm_q);
+    if (!TS) tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_x);
   }
   if (warp == 1) tmem_alloc_512(smem_u32(tmem_slot));
@@ -173,8 +206,10 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      mbar_arrive_expect_tx(bar_q, uint32_t(ks) * K2_SLICE);
-      for (int s = 0; s < ks; ++s) tma_load_2d(q_s + s * K2_SLICE, &tm_q, bar_q, s * 64, qt * K2_BM);
+      if constexpr (!TS) {
+        mbar_arrive_expect_tx(bar_q, uint32_t(ks) * K2_SLICE);
+        for (int s = 0; s < ks; ++s) tma_load_2d(q_s + s * K2_SLICE, &tm_q, bar_q, s * 64, qt * K2_BM);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int t = rs; t < ntiles; t += p.n_rslots) {
@@ -201,15 +236,22 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       for (int t = rs; t < ntiles; t += p.n_rslots) {
         mbar_wait(bar_tempty + acc * 8, acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + uint32_t(acc) * K2_NT;
+        const uint32_t d_tmem = tmem_base + acc_col0 + uint32_t(acc) * K2_NT;
         for (int s = 0; s < ks; ++s) {
           mbar_wait(bar_full + stage * 8, phase);
           tc_fence_after();
-          const uint64_t a_desc = umma_smem_desc(q_s + s * K2_SLICE);
           const uint64_t b_desc = umma_smem_desc(st_s + stage * K2_SLICE);
+          if constexpr (TS) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)  // 64-element slice = 4 x UMMA_K(16); +32 B per step inside the swizzle atom
-            umma_f16(d_tmem, a_desc + uint64_t(kk * 2), b_desc + uint64_t(kk * 2), idesc, uint32_t((s | kk) != 0));
+            for (int kk = 0; kk < 4; ++kk)  // 16 bf16 of K = 8 packed TMEM columns of the query tile
+              umma_f16_ts(d_tmem, tmem_base + uint32_t(s * 32 + kk * 8), b_desc + uint64_t(kk * 2), idesc,
+                          uint32_t((s | kk) != 0));
+          } else {
+            const uint64_t a_desc = umma_smem_desc(q_s + s * K2_SLICE);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)  // 64-element slice = 4 x UMMA_K(16); +32 B per step inside the swizzle atom
+              umma_f16(d_tmem, a_desc + uint64_t(kk * 2), b_desc + uint64_t(kk * 2), idesc, uint32_t((s | kk) != 0));
+          }
           umma_commit(bar_empty + stage * 8);
           if (++stage == nstages) {
             stage = 0;
@@ -217,7 +259,7 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           }
         }
         umma_commit(bar_tfull + acc * 8);
-        if (++acc == K2_ACC) {
+        if (++acc == NACC) {
           acc = 0;
           acc_phase ^= 1u;
         }
@@ -225,12 +267,34 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     }
   } else {
     // ------------------------------------------------------------------ epilogue: thread = query
-    const int quarter = warp & 3;              // TMEM lane quarter this warp may read
+    const int quarter = warp & 3;              // TMEM lane quarter this warp may access
     const int ql = quarter * 32 + lane;        // query within the tile
+    const int qglob = qt * K2_BM + ql;         // query within this launch
+    const bool live = qglob < p.B;
+    const bool warp_live = qt * K2_BM + quarter * 32 < p.B;   // any live query in this warp
+    if constexpr (TS) {
+      // stage the (already normalised, bf16) query tile into tensor memory: lane = query, column c = elements 2c, 2c+1
+      const uint32_t* qsrc = reinterpret_cast<const uint32_t*>(p.qbf16) + size_t(live ? qglob : 0) * (ks * 32);
+      for (int c = 0; c < ks; ++c) {
+        uint32_t w[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          uint4 x = live ? *reinterpret_cast<const uint4*>(qsrc + c * 32 + j) : make_uint4(0u, 0u, 0u, 0u);
+          w[j] = x.x; w[j + 1] = x.y; w[j + 2] = x.z; w[j + 3] = x.w;
+        }
+        tmem_st_x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c * 32), w);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_q);
+    }
     uint64_t* mine = lists + ql;               // my sorted list: mine[j * 128], j = 0 .. k-1 (best first)
     for (int j = 0; j < k; ++j) mine[size_t(j) * K2_BM] = 0ull;
     uint64_t thr_key = 0ull;
-    float thr_f = -INFINITY;
+    // Rows reach a thread in ascending order, so an equal score can never displace a held one: the strict
+    // compare `m > thr_f` is exact.  Padding queries never pass.
+    float thr_f = live ? -INFINITY : INFINITY;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = rs; t < ntiles; t += p.n_rslots) {
@@ -238,36 +302,35 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       const int nvalid = int(min(uint32_t(K2_NT), p.row_end - row0));
       mbar_wait(bar_tfull + acc * 8, acc_phase);
       tc_fence_after();
+      if (warp_live) {
 #pragma unroll 1
-      for (int c = 0; c < K2_NT / 32; ++c) {
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld_x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * K2_NT + c * 32), v);
-        tmem_wait_ld();
-        if constexpr (DUMP) {
-          const int64_t qrow = int64_t(qt) * K2_BM + ql;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = c * 32 + j;
-            if (col < nvalid && qt * K2_BM + ql < p.B) p.dump[qrow * p.dump_ld + int64_t(row0 - p.row_begin) + col] = __uint_as_float(v[j]);
-          }
-        } else {
-          if (nvalid < K2_NT) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c * 32 + j >= nvalid) v[j] = 0xFF800000u;  // -inf: rows past the segment end
-          }
-          float m = __uint_as_float(v[0]);
-#pragma unroll
-          for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
-          if (m >= thr_f) {
+        for (int c = 0; c < K2_NT / 32; ++c) {
+          uint32_t v[32];
+          __syncwarp();
+          tmem_ld_x32(tmem_base + (uint32_t(quarter * 32) << 16) + acc_col0 + uint32_t(acc * K2_NT + c * 32), v);
+          tmem_wait_ld();
+          if constexpr (DUMP) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float s = __uint_as_float(v[j]);
-              if (s >= thr_f && s > -INFINITY) {
-                const uint64_t key = make_key(s, row0 + uint32_t(c * 32 + j));
-                if (key > thr_key) {
-                  thr_key = k2_list_insert(mine, k, key);
+              const int col = c * 32 + j;
+              if (col < nvalid && live)
+                p.dump[int64_t(qglob) * p.dump_ld + int64_t(row0 - p.row_begin) + col] = __uint_as_float(v[j]);
+            }
+          } else {
+            if (nvalid < K2_NT) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c * 32 + j >= nvalid) v[j] = 0xFF800000u;  // -inf: rows past the segment end
+            }
+            float m = __uint_as_float(v[0]);
+#pragma unroll
+            for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+            if (m > thr_f) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float s = __uint_as_float(v[j]);
+                if (s > thr_f) {
+                  thr_key = k2_list_insert(mine, k, make_key(s, row0 + uint32_t(c * 32 + j)));
                   thr_f = thr_key ? key_score(thr_key) : -INFINITY;
                 }
               }
@@ -278,7 +341,7 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + acc * 8);
-      if (++acc == K2_ACC) {
+      if (++acc == NACC) {
         acc = 0;
         acc_phase ^= 1u;
       }
@@ -393,8 +456,8 @@ inline size_t umma_workspace_bytes(int sm_count, int dim, int B, int k) {
 inline int umma_launches_per_search() { return 3; }
 
 // smem plan: query tile + ring + lists + barriers
-inline int umma_plan_stages(int dim, int k, size_t* smem_bytes) {
-  const int ks = dim / 64;
+inline int umma_plan_stages(int dim, int k, size_t* smem_bytes, bool ts = false) {
+  const int ks = ts ? 0 : dim / 64;
   const size_t fixed = size_t(ks) * K2_SLICE + size_t(k) * K2_BM * 8 + (2 * K2_MAX_STAGES + 2 * K2_ACC + 2) * 8 + 1024;
   int stages = int((size_t(K2_SMEM_LIMIT) - fixed) / K2_SLICE);
   stages = std::min(stages, K2_MAX_STAGES);
@@ -425,16 +488,21 @@ inline int umma_search(UmmaIndexState& st, const void* rows, int64_t n_rows, int
     st.rows = rows;
     st.n_rows = n_rows;
   }
+  // A operand from tensor memory unless MMR_UMMA_MODE=ss asks for the shared-memory-operand variant
+  const char* mode = getenv("MMR_UMMA_MODE");
+  const bool ts = !(mode && mode[0] == 's') && dim / 2 + 2 * K2_NT <= 512;
   size_t smem_bytes = 0;
-  const int stages = umma_plan_stages(dim, k, &smem_bytes);
+  const int stages = umma_plan_stages(dim, k, &smem_bytes, ts);
   if (stages < 2) {
     err = "K2: shared memory plan does not fit";
     return MMR_ERR_UNSUPPORTED;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(scan_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_LIMIT);
-    cudaFuncSetAttribute(scan_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_LIMIT);
+    cudaFuncSetAttribute(scan_umma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_LIMIT);
+    cudaFuncSetAttribute(scan_umma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_LIMIT);
+    cudaFuncSetAttribute(scan_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_LIMIT);
+    cudaFuncSetAttribute(scan_umma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_LIMIT);
     attr_set = true;
   }
   __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(ws);
@@ -459,13 +527,16 @@ inline int umma_search(UmmaIndexState& st, const void* rows, int64_t n_rows, int
     const int64_t ntiles = (int64_t(r1) - r0 + K2_NT - 1) / K2_NT;
     p.n_rslots = int(std::max<int64_t>(1, std::min<int64_t>(sm_count / p.n_qtiles, ntiles)));
     p.partial = partial;
+    p.qbf16 = qb + size_t(q0) * dim;
     p.dump = dump ? dump + int64_t(q0) * dump_ld : nullptr;
     p.dump_ld = dump_ld;
     const int grid = p.n_qtiles * p.n_rslots;
     if (dump) {
-      scan_umma_kernel<true><<<grid, K2_THREADS, smem_bytes, stream>>>(tm_q, st.map, p);
+      if (ts) scan_umma_kernel<true, true><<<grid, K2_THREADS, smem_bytes, stream>>>(tm_q, st.map, p);
+      else scan_umma_kernel<true, false><<<grid, K2_THREADS, smem_bytes, stream>>>(tm_q, st.map, p);
     } else {
-      scan_umma_kernel<false><<<grid, K2_THREADS, smem_bytes, stream>>>(tm_q, st.map, p);
+      if (ts) scan_umma_kernel<false, true><<<grid, K2_THREADS, smem_bytes, stream>>>(tm_q, st.map, p);
+      else scan_umma_kernel<false, false><<<grid, K2_THREADS, smem_bytes, stream>>>(tm_q, st.map, p);
       const int wpb = 4;
       if (k <= 32)
         merge_partials_kernel<1><<<(bq + wpb - 1) / wpb, wpb * 32, 0, stream>>>(partial, p.n_qtiles, p.n_rslots, bq, k,

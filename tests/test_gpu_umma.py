@@ -23,8 +23,15 @@ def _bf16(x):
     return torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy()
 
 
+@pytest.fixture(params=["ts", "ss"])
+def umma_mode(request, monkeypatch):
+    """ts = query tile as the A operand in tensor memory (default); ss = both operands in shared memory."""
+    monkeypatch.setenv("MMR_UMMA_MODE", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("dim", [512, 384])
-def test_raw_scores_match_fp32_reference_of_same_inputs(mmr, dim):
+def test_raw_scores_match_fp32_reference_of_same_inputs(mmr, dim, umma_mode):
     """The tensor-core scores alone (no top-k): bf16 rows x bf16 unit queries, fp32 accumulate, against a plain
     fp32 matmul of the same bf16 values.  Catches descriptor / swizzle / TMEM-layout mistakes directly."""
     n = 70_000 + 37           # last tile is partial
@@ -45,7 +52,7 @@ def test_raw_scores_match_fp32_reference_of_same_inputs(mmr, dim):
 
 
 @pytest.mark.parametrize("b", [5, 8, 127, 128, 129, 300])
-def test_topk_matches_oracle(mmr, b):
+def test_topk_matches_oracle(mmr, b, umma_mode):
     rows = util.unit_rows(150_000, 512, seed=91, cone=0.3)
     ix = mmr.ResidentIndex.from_f32(rows, dtype="bf16")
     qs = util.queries(b, 512, cone=0.3)
