@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f16", "f32"])
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sweep", default="", help="extra batch sizes to report under 'sweep', e.g. 2,4,8")
+    ap.add_argument("--sweep", default="8,128,1024", help="extra batch sizes reported under 'sweep' (N=1 only)")
     return ap.parse_args()
 
 
@@ -303,16 +303,33 @@ def run_b200(args):
         ix.search(q_dev[i], k, out=(out_s, out_r))
     ev3.record()
     torch.cuda.synchronize(device)
-    n_launch = (B + 3) // 4 if lib.mmr_last_kernel() == 1 else 1
+    n_launch = (B + 3) // 4 if lib.mmr_last_kernel() == 1 else 1  # K2: the scan kernel dominates its 5 launches
     kernel_ms = ev2.elapsed_time(ev3) / (K * n_launch)
     hbm_peak, tf_peak, peak_kind = measured_peaks()
     algo_bytes = (hi - lo) * D * esize
-    achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_kind": f"of {peak_kind}", "frac_of_nominal_8TBs": achieved / 8000.0,
-                "kernel": {1: "scan_stream_kernel (K1)", 2: "scan_umma_kernel (K2)", 3: "scan_stream_kernel varlen"}.get(lib.mmr_last_kernel()),
-                "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo_bytes,
-                "tensor_tflops": 2.0 * B * (hi - lo) * D / (kernel_ms * n_launch * 1e-3) / 1e12}
+
+    def roof(b, ms_per_pass, n_launches=1):
+        """Roofline entry for one pass of b queries over this GPU's rows in ms_per_pass."""
+        gbs = algo_bytes / (ms_per_pass * 1e-3) / 1e9
+        tfl = 2.0 * b * (hi - lo) * D / (ms_per_pass * 1e-3) / 1e12
+        tensor_bound = tfl / tf_peak > gbs / hbm_peak
+        out = {"bound": "tensor" if tensor_bound else "hbm",
+               "achieved": tfl if tensor_bound else gbs, "peak": tf_peak if tensor_bound else hbm_peak,
+               "unit": "TFLOP/s" if tensor_bound else "GB/s",
+               "frac": (tfl / tf_peak) if tensor_bound else (gbs / hbm_peak), "traffic": None,
+               "peak_kind": f"of {peak_kind}" + (" (cuBLAS bf16 burst)" if tensor_bound else " (copy)"),
+               "hbm_GBs": gbs, "tensor_tflops": tfl, "frac_of_nominal_8TBs": gbs / 8000.0,
+               "algorithmic_bytes_per_launch": algo_bytes, "algorithmic_flops_per_launch": 2.0 * b * (hi - lo) * D / n_launches}
+        return out
+
+    kern = lib.mmr_last_kernel()
+    roofline = roof(B, kernel_ms * n_launch, n_launch)
+    roofline["kernel"] = {1: "scan_stream_kernel (K1, bulk-copy streaming dot + warp top-k)",
+                          2: "scan_umma_kernel (K2, tcgen05/TMEM contraction + fused top-k)",
+                          3: "scan_stream_kernel varlen"}.get(kern)
+    roofline["kernel_ms"] = kernel_ms
+    if kern == 1 and B == 1 and D == 512 and args.dtype == "bf16" and hi - lo == 10_000_000:
+        roofline["traffic"] = 10_240_285_000  # dram__bytes_read+write per launch, ncu --set full, profiles/r01_k1_summary.md
 
     # end to end through the host-buffer C-ABI call (pinned staging, H2D, scan, D2H, sync) -- rank-local shard;
     # for N > 1 the gather + merge of the tiny [G,B,k] lists is included via the device path above.
@@ -364,8 +381,9 @@ def run_b200(args):
         e1.record()
         torch.cuda.synchronize(device)
         ms = e0.elapsed_time(e1) / reps
-        sweep.append({"batch": b2, "ms_per_step": ms, "queries_per_s": b2 / (ms * 1e-3),
-                      "hbm_GBs": algo_bytes / (ms * 1e-3) / 1e9, "tensor_tflops": 2.0 * b2 * (hi - lo) * D / (ms * 1e-3) / 1e12,
+        r2 = roof(b2, ms)
+        sweep.append({"batch": b2, "ms_per_step": ms, "queries_per_s": b2 / (ms * 1e-3), "bound": r2["bound"],
+                      "frac": r2["frac"], "hbm_GBs": r2["hbm_GBs"], "tensor_tflops": r2["tensor_tflops"],
                       "kernel": lib.mmr_last_kernel()})
 
     cpu_baseline = None

@@ -107,6 +107,11 @@ int mmr_search_host(mmr_index* index, const float* queries_host, const int32_t* 
  */
 int mmr_merge_topk(const float* scores_dev, const int64_t* rows_dev, int32_t G, int32_t B, int32_t k,
                    float* out_scores_dev, int64_t* out_rows_dev, void* stream);
+/* Same, shard g's [B, k] block starting at element g * stride of each array: lets the merge read the
+ * all-gathered wire buffer ([G][scores | rows]) in place. */
+int mmr_merge_topk_strided(const float* scores_dev, const int64_t* rows_dev, int64_t score_shard_stride,
+                           int64_t row_shard_stride, int32_t G, int32_t B, int32_t k, float* out_scores_dev,
+                           int64_t* out_rows_dev, void* stream);
 
 /*
  * Fusion + gate (K5): _fuse_results with no rerank scores (reference app/ml/retrieve.py:158-195) and

@@ -51,12 +51,14 @@ __global__ void convert_rows_kernel(const float* __restrict__ src, E* __restrict
 
 // ------------------------------------------------------------------------------------------------
 // K4 -- merge G shard-local top-k lists into one.  Inputs are what each shard's scan wrote:
-// scores [G, B, k] f32 and rows [G, B, k] i64 (global ordinals, -1 = empty).  One warp per query.
+// scores [G, B, k] f32 and rows [G, B, k] i64 (global ordinals, -1 = empty), shard g starting at element
+// g * score_stride / g * row_stride (so the gathered wire buffers can be read in place).  One warp per query.
 // Same total order as everywhere else: (score desc, row asc); result is independent of G.
 // ------------------------------------------------------------------------------------------------
 template <int KPL>
-__global__ void merge_shards_kernel(const float* __restrict__ scores, const int64_t* __restrict__ rows, int G, int B,
-                                    int k, float* __restrict__ out_scores, int64_t* __restrict__ out_rows) {
+__global__ void merge_shards_kernel(const float* __restrict__ scores, const int64_t* __restrict__ rows,
+                                    int64_t score_stride, int64_t row_stride, int G, int B, int k,
+                                    float* __restrict__ out_scores, int64_t* __restrict__ out_rows) {
   const int lane = threadIdx.x & 31;
   const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (qi >= B) return;
@@ -71,10 +73,10 @@ __global__ void merge_shards_kernel(const float* __restrict__ scores, const int6
     uint64_t key = 0ull;
     if (valid) {
       const int g = i / per, j = i % per;
-      const size_t o = (size_t(g) * B + qi) * k + j;
-      const int64_t r = rows[o];
+      const size_t o = size_t(qi) * k + j;
+      const int64_t r = rows[size_t(g) * row_stride + o];
       valid = r >= 0;
-      if (valid) key = make_key(scores[o], uint32_t(r));
+      if (valid) key = make_key(scores[size_t(g) * score_stride + o], uint32_t(r));
     }
     thr = m.offer(key, valid, thr, k, lane);
   }

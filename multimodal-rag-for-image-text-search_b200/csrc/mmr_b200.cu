@@ -502,21 +502,32 @@ extern "C" int mmr_debug_umma_scores(const mmr_index*, const float*, int32_t, in
 #endif
 
 // ------------------------------------------------------------------------------------------------ K4 / K5
-extern "C" int mmr_merge_topk(const float* scores_dev, const int64_t* rows_dev, int32_t G, int32_t B, int32_t k,
-                              float* out_scores_dev, int64_t* out_rows_dev, void* stream) {
+extern "C" int mmr_merge_topk_strided(const float* scores_dev, const int64_t* rows_dev, int64_t score_shard_stride,
+                                      int64_t row_shard_stride, int32_t G, int32_t B, int32_t k, float* out_scores_dev,
+                                      int64_t* out_rows_dev, void* stream) {
   if (G <= 0 || B <= 0) return fail(MMR_ERR_INVALID, "G and B must be >= 1");
   if (k < 1 || k > MMR_MAX_K) return fail(MMR_ERR_INVALID, "k must be in [1, %d]", MMR_MAX_K);
   if (!scores_dev || !rows_dev || !out_scores_dev || !out_rows_dev) return fail(MMR_ERR_INVALID, "NULL buffer");
+  if (score_shard_stride < int64_t(B) * k || row_shard_stride < int64_t(B) * k)
+    return fail(MMR_ERR_INVALID, "shard stride smaller than B*k");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int wpb = 4;
   const int blocks = (B + wpb - 1) / wpb;
   if (k <= 32)
-    merge_shards_kernel<1><<<blocks, wpb * 32, 0, st>>>(scores_dev, rows_dev, G, B, k, out_scores_dev, out_rows_dev);
+    merge_shards_kernel<1><<<blocks, wpb * 32, 0, st>>>(scores_dev, rows_dev, score_shard_stride, row_shard_stride, G, B,
+                                                        k, out_scores_dev, out_rows_dev);
   else
-    merge_shards_kernel<2><<<blocks, wpb * 32, 0, st>>>(scores_dev, rows_dev, G, B, k, out_scores_dev, out_rows_dev);
+    merge_shards_kernel<2><<<blocks, wpb * 32, 0, st>>>(scores_dev, rows_dev, score_shard_stride, row_shard_stride, G, B,
+                                                        k, out_scores_dev, out_rows_dev);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return MMR_OK;
+}
+
+extern "C" int mmr_merge_topk(const float* scores_dev, const int64_t* rows_dev, int32_t G, int32_t B, int32_t k,
+                              float* out_scores_dev, int64_t* out_rows_dev, void* stream) {
+  return mmr_merge_topk_strided(scores_dev, rows_dev, int64_t(B) * k, int64_t(B) * k, G, B, k, out_scores_dev,
+                                out_rows_dev, stream);
 }
 
 extern "C" int mmr_fuse(const float* text_scores_dev, const int64_t* text_rows_dev, int32_t kt,

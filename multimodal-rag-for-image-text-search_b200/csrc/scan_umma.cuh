@@ -47,6 +47,9 @@ struct UmmaParams {
   int32_t n_qtiles, n_rslots;
   uint64_t* partial;  // [n_qtiles * n_rslots][128][k]
   const void* qbf16;  // TS mode: normalised bf16 queries of this launch, [B][D]
+  const float* floor; // per query: a proven lower bound of its final k-th best score (nullptr = none)
+  float* probe_out;   // probe pass: [n_qtiles * n_rslots][128] best score seen by each CTA (nullptr = real scan)
+  int32_t probe_tiles;  // probe pass: row tiles per CTA
   float* dump;        // DUMP mode: raw scores [B][dump_ld]
   int64_t dump_ld;
 };
@@ -62,6 +65,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+// One lane of a converged warp (always the same one): the thread that issues TMA / tcgen05.mma / commit.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -112,18 +125,35 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_m128_n128() {
   return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(K2_NT >> 3) << 17) | (uint32_t(K2_BM >> 4) << 24);
 }
 
-// Rare path of the epilogue: insert `key` into this thread's sorted list (best first, stride K2_BM in shared
-// memory) and return the new k-th key.  Kept out of line so the 32-way unrolled caller stays small.
-__device__ __noinline__ uint64_t k2_list_insert(uint64_t* mine, int k, uint64_t key) {
-  int pos = k - 1;
-  while (pos > 0) {
-    const uint64_t prev = mine[size_t(pos - 1) * K2_BM];
-    if (prev >= key) break;
-    mine[size_t(pos) * K2_BM] = prev;
-    --pos;
+// Rare path of the epilogue: put `key` into this thread's candidate list (k slots, stride K2_BM in shared
+// memory, unsorted) by overwriting the current minimum, and return the new minimum = the thread's k-th best key
+// (0 while fewer than k candidates are held).  Replace-min keeps the loads independent (no shifting chain);
+// merge_partials_kernel does the final ordering.  *meta = held count | position of the minimum << 8.
+__device__ __noinline__ uint64_t k2_list_insert(uint64_t* mine, uint32_t* meta, int k, uint64_t key) {
+  const uint32_t m = *meta;
+  int count = int(m & 0xffu);
+  if (count < k) {
+    mine[size_t(count) * K2_BM] = key;
+    ++count;
+    if (count < k) {
+      *meta = uint32_t(count);
+      return 0ull;
+    }
+  } else {
+    mine[size_t(m >> 8) * K2_BM] = key;
   }
-  mine[size_t(pos) * K2_BM] = key;
-  return mine[size_t(k - 1) * K2_BM];
+  uint64_t mv = ~0ull;
+  int mp = 0;
+#pragma unroll 4
+  for (int j = 0; j < k; ++j) {
+    const uint64_t x = mine[size_t(j) * K2_BM];
+    if (x < mv) {
+      mv = x;
+      mp = j;
+    }
+  }
+  *meta = uint32_t(count) | (uint32_t(mp) << 8);
+  return mv;
 }
 
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
@@ -169,7 +199,8 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   const uint32_t q_s = smem_u32(smem);
   const uint32_t st_s = q_s + uint32_t(qslices) * K2_SLICE;
   uint64_t* lists = reinterpret_cast<uint64_t*>(smem + size_t(qslices + nstages) * K2_SLICE);  // [k][128]
-  uint64_t* bars = lists + size_t(k) * K2_BM;
+  uint32_t* metas = reinterpret_cast<uint32_t*>(lists + size_t(k) * K2_BM);                     // [128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(metas + K2_BM);
   const uint32_t bar_full = smem_u32(bars);                      // [K2_MAX_STAGES]
   const uint32_t bar_empty = bar_full + K2_MAX_STAGES * 8;       // [K2_MAX_STAGES]
   const uint32_t bar_tfull = bar_empty + K2_MAX_STAGES * 8;      // [K2_ACC]
@@ -180,7 +211,9 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   const int qt = blockIdx.x % p.n_qtiles;
   const int rs = blockIdx.x / p.n_qtiles;
   const uint32_t nrows = p.row_end - p.row_begin;
-  const int ntiles = int((nrows + K2_NT - 1) / K2_NT);
+  const int ntiles_all = int((nrows + K2_NT - 1) / K2_NT);
+  // probe pass: only the first probe_tiles tiles of this CTA's strided sequence
+  const int ntiles = p.probe_out ? min(ntiles_all, rs + p.probe_tiles * p.n_rslots) : ntiles_all;
 
   if (threadIdx.x == 0) {
     if ((q_s & 1023u) != 0) __trap();  // SWIZZLE_128B operands need 1024-byte alignment
@@ -205,64 +238,78 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      if constexpr (!TS) {
+    // The whole warp runs the (warp-uniform) loop; one elected lane issues the copies.  Keeping control flow
+    // uniform lets the compiler hold addresses / coordinates in uniform registers.
+    const bool leader = elect_one();
+    if constexpr (!TS) {
+      if (leader) {
         mbar_arrive_expect_tx(bar_q, uint32_t(ks) * K2_SLICE);
         for (int s = 0; s < ks; ++s) tma_load_2d(q_s + s * K2_SLICE, &tm_q, bar_q, s * 64, qt * K2_BM);
       }
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = rs; t < ntiles; t += p.n_rslots) {
-        const int32_t row0 = int32_t(p.row_begin + uint32_t(t) * K2_NT);
-        for (int s = 0; s < ks; ++s) {
-          mbar_wait(bar_empty + stage * 8, phase ^ 1u);
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = rs; t < ntiles; t += p.n_rslots) {
+      const int32_t row0 = int32_t(p.row_begin + uint32_t(t) * K2_NT);
+      for (int s = 0; s < ks; ++s) {
+        mbar_wait(bar_empty + stage * 8, phase ^ 1u);
+        if (leader) {
           mbar_arrive_expect_tx(bar_full + stage * 8, K2_SLICE);
           tma_load_2d(st_s + stage * K2_SLICE, &tm_x, bar_full + stage * 8, s * 64, row0);
-          if (++stage == nstages) {
-            stage = 0;
-            phase ^= 1u;
-          }
+        }
+        __syncwarp();
+        if (++stage == nstages) {
+          stage = 0;
+          phase ^= 1u;
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_m128_n128();
-      mbar_wait(bar_q, 0);
+    // Warp-uniform loop, one elected lane issues tcgen05.mma and the commits (same lane for both: a commit
+    // tracks the MMAs of the thread that executes it).
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = umma_idesc_bf16_m128_n128();
+    mbar_wait(bar_q, 0);
+    tc_fence_after();
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int t = rs; t < ntiles; t += p.n_rslots) {
+      mbar_wait(bar_tempty + acc * 8, acc_phase ^ 1u);
       tc_fence_after();
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int t = rs; t < ntiles; t += p.n_rslots) {
-        mbar_wait(bar_tempty + acc * 8, acc_phase ^ 1u);
+      const uint32_t d_tmem = tmem_base + acc_col0 + uint32_t(acc) * K2_NT;
+      for (int s = 0; s < ks; ++s) {
+        mbar_wait(bar_full + stage * 8, phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc_col0 + uint32_t(acc) * K2_NT;
-        for (int s = 0; s < ks; ++s) {
-          mbar_wait(bar_full + stage * 8, phase);
-          tc_fence_after();
-          const uint64_t b_desc = umma_smem_desc(st_s + stage * K2_SLICE);
-          if constexpr (TS) {
+        const uint64_t b_desc = umma_smem_desc(st_s + stage * K2_SLICE);
+        if constexpr (TS) {
+          if (leader) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)  // 16 bf16 of K = 8 packed TMEM columns of the query tile
               umma_f16_ts(d_tmem, tmem_base + uint32_t(s * 32 + kk * 8), b_desc + uint64_t(kk * 2), idesc,
                           uint32_t((s | kk) != 0));
-          } else {
-            const uint64_t a_desc = umma_smem_desc(q_s + s * K2_SLICE);
+            umma_commit(bar_empty + stage * 8);
+          }
+        } else {
+          const uint64_t a_desc = umma_smem_desc(q_s + s * K2_SLICE);
+          if (leader) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)  // 64-element slice = 4 x UMMA_K(16); +32 B per step inside the swizzle atom
               umma_f16(d_tmem, a_desc + uint64_t(kk * 2), b_desc + uint64_t(kk * 2), idesc, uint32_t((s | kk) != 0));
-          }
-          umma_commit(bar_empty + stage * 8);
-          if (++stage == nstages) {
-            stage = 0;
-            phase ^= 1u;
+            umma_commit(bar_empty + stage * 8);
           }
         }
-        umma_commit(bar_tfull + acc * 8);
-        if (++acc == NACC) {
-          acc = 0;
-          acc_phase ^= 1u;
+        __syncwarp();
+        if (++stage == nstages) {
+          stage = 0;
+          phase ^= 1u;
         }
+      }
+      if (leader) umma_commit(bar_tfull + acc * 8);
+      __syncwarp();
+      if (++acc == NACC) {
+        acc = 0;
+        acc_phase ^= 1u;
       }
     }
   } else {
@@ -289,12 +336,22 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_q);
     }
-    uint64_t* mine = lists + ql;               // my sorted list: mine[j * 128], j = 0 .. k-1 (best first)
+    uint64_t* mine = lists + ql;               // my candidate list: mine[j * 128], j = 0 .. k-1 (unsorted)
+    uint32_t* meta = metas + ql;
     for (int j = 0; j < k; ++j) mine[size_t(j) * K2_BM] = 0ull;
+    *meta = 0u;
     uint64_t thr_key = 0ull;
     // Rows reach a thread in ascending order, so an equal score can never displace a held one: the strict
     // compare `m > thr_f` is exact.  Padding queries never pass.
-    float thr_f = live ? -INFINITY : INFINITY;
+    // A proven lower bound of the final k-th score (from the probe pass) pre-loads the filter, so the scan does
+    // not pay the warm-up in which every row beats an empty list.  `s >= floor` must pass: use the float just below.
+    float thr_floor = -INFINITY;
+    if (p.floor != nullptr && live) {
+      const float f = p.floor[qglob];
+      if (f > -INFINITY) thr_floor = f32_from_orderable(f32_orderable(f) - 1u);
+    }
+    float thr_f = live ? thr_floor : INFINITY;
+    float best = -INFINITY;  // probe pass
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = rs; t < ntiles; t += p.n_rslots) {
@@ -322,16 +379,30 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
               for (int j = 0; j < 32; ++j)
                 if (c * 32 + j >= nvalid) v[j] = 0xFF800000u;  // -inf: rows past the segment end
             }
-            float m = __uint_as_float(v[0]);
+            // two-level filter: max per group of 8 columns, then max of the 4 groups against my k-th best
+            float gm[4];
 #pragma unroll
-            for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
-            if (m > thr_f) {
+            for (int g = 0; g < 4; ++g) {
+              float x = __uint_as_float(v[g * 8]);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float s = __uint_as_float(v[j]);
-                if (s > thr_f) {
-                  thr_key = k2_list_insert(mine, k, make_key(s, row0 + uint32_t(c * 32 + j)));
-                  thr_f = thr_key ? key_score(thr_key) : -INFINITY;
+              for (int j = 1; j < 8; ++j) x = fmaxf(x, __uint_as_float(v[g * 8 + j]));
+              gm[g] = x;
+            }
+            const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+            if (p.probe_out != nullptr) {
+              best = fmaxf(best, m);
+            } else if (m > thr_f) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                if (gm[g] > thr_f) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const float s = __uint_as_float(v[g * 8 + j]);
+                    if (s > thr_f) {
+                      thr_key = k2_list_insert(mine, meta, k, make_key(s, row0 + uint32_t(c * 32 + g * 8 + j)));
+                      thr_f = thr_key ? fmaxf(thr_floor, key_score(thr_key)) : thr_floor;
+                    }
+                  }
                 }
               }
             }
@@ -347,8 +418,12 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       }
     }
     if constexpr (!DUMP) {
-      uint64_t* dst = p.partial + (size_t(qt * p.n_rslots + rs) * K2_BM + ql) * k;
-      for (int j = 0; j < k; ++j) dst[j] = mine[size_t(j) * K2_BM];
+      if (p.probe_out != nullptr) {
+        p.probe_out[size_t(qt * p.n_rslots + rs) * K2_BM + ql] = best;
+      } else {
+        uint64_t* dst = p.partial + (size_t(qt * p.n_rslots + rs) * K2_BM + ql) * k;
+        for (int j = 0; j < k; ++j) dst[j] = mine[size_t(j) * K2_BM];
+      }
     }
   }
   tc_fence_before();
@@ -389,6 +464,27 @@ __global__ void merge_partials_kernel(const uint64_t* __restrict__ partial, int 
       out_rows[size_t(q) * k + pos] = key ? int64_t(key_row(key)) + row_base : int64_t(-1);
     }
   }
+}
+
+// Probe reduction: per query, the k-th largest of the per-CTA best scores.  The RS values belong to RS distinct
+// rows, so this is a lower bound of the query's final k-th best score (-inf when fewer than k CTAs probed).
+template <int KPL>
+__global__ void probe_floor_kernel(const float* __restrict__ probe, int n_qtiles, int n_rslots, int B, int k,
+                                   float* __restrict__ floor) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= B) return;
+  const int qt = q / K2_BM, ql = q % K2_BM;
+  WarpTopK<KPL> m;
+  m.clear();
+  uint64_t thr = 0ull;
+  for (int i0 = 0; i0 < n_rslots; i0 += 32) {
+    const int rs = i0 + lane;
+    const bool valid = rs < n_rslots;
+    const float v = valid ? probe[size_t(qt * n_rslots + rs) * K2_BM + ql] : -INFINITY;
+    thr = m.offer(make_key(v, uint32_t(rs)), valid && v > -INFINITY, thr, k, lane);
+  }
+  if (lane == 0) floor[q] = thr ? key_score(thr) : -INFINITY;
 }
 
 // fp32 queries -> L2-normalised bf16 (LanceDBStore._normalize, then narrowed for the tensor cores). Warp per query.
@@ -450,15 +546,17 @@ inline int umma_qtiles(int B) { return (B + K2_BM - 1) / K2_BM; }
 inline size_t umma_workspace_bytes(int sm_count, int dim, int B, int k) {
   const int qtiles = std::min(umma_qtiles(B), sm_count);
   const int ctas = std::max(sm_count, qtiles);
-  return umma_align(size_t(B) * dim * 2) + umma_align(size_t(ctas) * K2_BM * k * 8) + 256;
+  return umma_align(size_t(B) * dim * 2) + umma_align(size_t(ctas) * K2_BM * k * 8) +
+         umma_align(size_t(ctas) * K2_BM * 4) + umma_align(size_t(B) * 4) + 256;
 }
 
-inline int umma_launches_per_search() { return 3; }
+inline int umma_launches_per_search() { return 5; }  // prep, probe, floor, scan, merge
 
 // smem plan: query tile + ring + lists + barriers
 inline int umma_plan_stages(int dim, int k, size_t* smem_bytes, bool ts = false) {
   const int ks = ts ? 0 : dim / 64;
-  const size_t fixed = size_t(ks) * K2_SLICE + size_t(k) * K2_BM * 8 + (2 * K2_MAX_STAGES + 2 * K2_ACC + 2) * 8 + 1024;
+  const size_t fixed = size_t(ks) * K2_SLICE + size_t(k) * K2_BM * 8 + K2_BM * 4 +
+                       (2 * K2_MAX_STAGES + 2 * K2_ACC + 2) * 8 + 1024;
   int stages = int((size_t(K2_SMEM_LIMIT) - fixed) / K2_SLICE);
   stages = std::min(stages, K2_MAX_STAGES);
   if (smem_bytes) *smem_bytes = fixed + size_t(std::max(stages, 0)) * K2_SLICE;
@@ -467,7 +565,7 @@ inline int umma_plan_stages(int dim, int k, size_t* smem_bytes, bool ts = false)
 
 // K2 wants bf16 rows, dim % 64 == 0, enough rows to fill the grid, and more queries than K1 serves in one pass.
 inline bool umma_preferred(int dtype, int dim, int B, int k, int64_t nrows) {
-  if (dtype != MMR_BF16 || dim % 64 != 0 || B <= 4) return false;
+  if (dtype != MMR_BF16 || dim % 64 != 0 || B < 3) return false;  // K1 keeps B <= 2 (fp32 queries, one launch)
   if (nrows < 64 * 1024 || nrows >= (int64_t(1) << 31)) return false;
   return umma_plan_stages(dim, k, nullptr) >= 2;
 }
@@ -488,9 +586,15 @@ inline int umma_search(UmmaIndexState& st, const void* rows, int64_t n_rows, int
     st.rows = rows;
     st.n_rows = n_rows;
   }
-  // A operand from tensor memory unless MMR_UMMA_MODE=ss asks for the shared-memory-operand variant
+  // Operand placement, chosen from measurements on B200 (profiles/r01_k2_sweep.md): one query tile (B <= 128) is
+  // HBM-bound and fastest with both operands in shared memory and 4 accumulators; several query tiles are
+  // tensor-bound and fastest with the query tile in tensor memory (half the shared-memory reads per MMA, 13-deep
+  // ring).  MMR_UMMA_MODE=ss|ts overrides.
   const char* mode = getenv("MMR_UMMA_MODE");
-  const bool ts = !(mode && mode[0] == 's') && dim / 2 + 2 * K2_NT <= 512;
+  bool ts = umma_qtiles(B) > 1;
+  if (mode && mode[0] == 's') ts = false;
+  if (mode && mode[0] == 't') ts = true;
+  if (dim / 2 + 2 * K2_NT > 512) ts = false;
   size_t smem_bytes = 0;
   const int stages = umma_plan_stages(dim, k, &smem_bytes, ts);
   if (stages < 2) {
@@ -507,6 +611,10 @@ inline int umma_search(UmmaIndexState& st, const void* rows, int64_t n_rows, int
   }
   __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(ws);
   uint64_t* partial = reinterpret_cast<uint64_t*>(ws + umma_align(size_t(B) * dim * 2));
+  const int ctas_max = std::max(sm_count, std::min(umma_qtiles(B), sm_count));
+  float* probe = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(partial) + umma_align(size_t(ctas_max) * K2_BM * k * 8));
+  float* floor = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(probe) + umma_align(size_t(ctas_max) * K2_BM * 4));
+  const char* noprobe = getenv("MMR_UMMA_NOPROBE");
   prep_queries_kernel<<<(B + 3) / 4, 128, 0, stream>>>(queries, qb, B, dim);
   const int max_q_per_pass = sm_count * K2_BM;
   for (int q0 = 0; q0 < B; q0 += max_q_per_pass) {
@@ -531,6 +639,19 @@ inline int umma_search(UmmaIndexState& st, const void* rows, int64_t n_rows, int
     p.dump = dump ? dump + int64_t(q0) * dump_ld : nullptr;
     p.dump_ld = dump_ld;
     const int grid = p.n_qtiles * p.n_rslots;
+    // probe pass: worth it when every CTA streams many tiles (the warm-up it removes is ~k ln(n/k) inserts/thread)
+    const int64_t tiles_per_cta = ntiles / p.n_rslots;
+    if (!dump && !(noprobe && noprobe[0] == '1') && tiles_per_cta >= 64 && p.n_rslots >= k) {
+      UmmaParams pp = p;
+      pp.probe_out = probe;
+      pp.probe_tiles = int(std::max<int64_t>(2, std::min<int64_t>(16, tiles_per_cta / 32)));
+      if (ts) scan_umma_kernel<false, true><<<grid, K2_THREADS, smem_bytes, stream>>>(tm_q, st.map, pp);
+      else scan_umma_kernel<false, false><<<grid, K2_THREADS, smem_bytes, stream>>>(tm_q, st.map, pp);
+      const int wpb = 4;
+      if (k <= 32) probe_floor_kernel<1><<<(bq + wpb - 1) / wpb, wpb * 32, 0, stream>>>(probe, p.n_qtiles, p.n_rslots, bq, k, floor + q0);
+      else probe_floor_kernel<2><<<(bq + wpb - 1) / wpb, wpb * 32, 0, stream>>>(probe, p.n_qtiles, p.n_rslots, bq, k, floor + q0);
+      p.floor = floor + q0;
+    }
     if (dump) {
       if (ts) scan_umma_kernel<true, true><<<grid, K2_THREADS, smem_bytes, stream>>>(tm_q, st.map, p);
       else scan_umma_kernel<true, false><<<grid, K2_THREADS, smem_bytes, stream>>>(tm_q, st.map, p);

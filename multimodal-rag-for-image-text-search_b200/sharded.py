@@ -1,0 +1,125 @@
+"""Row-range sharding of one table over the GPUs of a box.
+
+One process per GPU (torch.distributed).  Every rank holds rows [bounds[r], bounds[r+1]) of the tenant-sorted
+table as a ResidentIndex with row_base = bounds[r]; queries are replicated; each rank scans its shard, the tiny
+per-shard results ([B, k] scores + rows, 12 B per hit) are all-gathered in ONE collective on a packed wire
+buffer, and every rank runs the K4 merge kernel on the gathered buffer in place.  The answer is bit-identical
+for every world size (same total order: score desc, row asc).
+
+The scan itself runs only on CUDA (no CPU fallback); the bounds / wire / gather logic here is backend-agnostic
+and is exercised with the gloo backend on CPU in tests/test_sharded_gloo.py.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_rows: int, world: int, align: int = 1) -> List[int]:
+    """Contiguous, balanced row ranges; interior bounds rounded to `align` rows."""
+    bounds = [0]
+    for r in range(1, world):
+        b = int(round(r * n_rows / world))
+        b = min(n_rows, (b + align - 1) // align * align)
+        bounds.append(max(b, bounds[-1]))
+    bounds.append(n_rows)
+    return bounds
+
+
+def split_segments(seg_offsets: Sequence[int], lo: int, hi: int) -> np.ndarray:
+    """Tenant segment table of the shard [lo, hi): global offsets clipped to the shard and made shard-local.
+    A tenant that straddles a shard boundary keeps its id on both sides (each GPU scans its slice)."""
+    seg = np.asarray(seg_offsets, dtype=np.int64)
+    return np.clip(seg, lo, hi) - lo
+
+
+class Wire:
+    """Packed per-rank result buffer: [scores f32 B*k | pad to 8 | rows i64 B*k] as one uint8 tensor."""
+
+    def __init__(self, b: int, k: int, device) -> None:
+        self.b, self.k = b, k
+        self.score_bytes = (b * k * 4 + 7) // 8 * 8
+        self.nbytes = self.score_bytes + b * k * 8
+        self.buf = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
+        self.scores = self.buf[: b * k * 4].view(torch.float32).view(b, k)
+        self.rows = self.buf[self.score_bytes:].view(torch.int64).view(b, k)
+
+
+class GatheredWire:
+    """world x Wire, gathered in place; views for the strided K4 merge."""
+
+    def __init__(self, wire: Wire, world: int) -> None:
+        self.world, self.wire = world, wire
+        self.buf = torch.zeros((world, wire.nbytes), dtype=torch.uint8, device=wire.buf.device)
+
+    def views(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        w = self.wire
+        scores = self.buf[:, : w.b * w.k * 4].view(torch.float32)      # [G, B*k], row stride nbytes/4
+        rows = self.buf[:, w.score_bytes:].view(torch.int64)            # [G, B*k], row stride nbytes/8
+        return scores, rows
+
+
+def gather_wire(wire: Wire, gathered: GatheredWire, group=None) -> None:
+    """The one exchange step of the path: all-gather of the packed per-shard top-k."""
+    dist.all_gather_into_tensor(gathered.buf.view(-1), wire.buf, group=group)
+
+
+def merge_gathered_numpy(gathered: GatheredWire) -> Tuple[np.ndarray, np.ndarray]:
+    """Host statement of the K4 merge for the CPU tests of the exchange logic (NOT a product path)."""
+    scores, rows = gathered.views()
+    w = gathered.wire
+    s = scores.cpu().numpy().reshape(gathered.world, w.b, w.k)
+    r = rows.cpu().numpy().reshape(gathered.world, w.b, w.k)
+    out_s = np.full((w.b, w.k), -np.inf, np.float32)
+    out_r = np.full((w.b, w.k), -1, np.int64)
+    for q in range(w.b):
+        cs, cr = s[:, q].reshape(-1), r[:, q].reshape(-1)
+        keep = cr >= 0
+        cs, cr = cs[keep], cr[keep]
+        order = np.lexsort((cr, -cs.astype(np.float64)))[: w.k]
+        out_s[q, : len(order)], out_r[q, : len(order)] = cs[order], cr[order]
+    return out_s, out_r
+
+
+class ShardedIndex:
+    """This rank's shard + the exchange.  `local` is a ResidentIndex built with row_base = bounds[rank]."""
+
+    def __init__(self, local, group=None) -> None:
+        self.local = local
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._wire: Optional[Wire] = None
+        self._gathered: Optional[GatheredWire] = None
+        self._out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+
+    def _buffers(self, b: int, k: int):
+        if self._wire is None or (self._wire.b, self._wire.k) != (b, k):
+            dev = self.local.device
+            self._wire = Wire(b, k, dev)
+            self._gathered = GatheredWire(self._wire, self.world)
+            self._out = (torch.empty((b, k), dtype=torch.float32, device=dev),
+                         torch.empty((b, k), dtype=torch.int64, device=dev))
+        return self._wire, self._gathered, self._out
+
+    def search(self, queries: torch.Tensor, k: int, segments=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Replicated queries [B, dim] -> global top-k (identical on every rank)."""
+        from . import _native as N
+        from .index import _stream_ptr
+
+        b = int(queries.shape[0]) if queries.dim() == 2 else 1
+        k = max(int(k), 1)
+        wire, gathered, out = self._buffers(b, k)
+        self.local.search(queries, k, segments, out=(wire.scores, wire.rows))
+        if self.world == 1:
+            return wire.scores, wire.rows
+        gather_wire(wire, gathered, self.group)
+        scores, rows = gathered.views()
+        dev = self.local.device
+        with torch.cuda.device(dev):
+            N.check(N.lib().mmr_merge_topk_strided(scores.data_ptr(), rows.data_ptr(), wire.nbytes // 4, wire.nbytes // 8,
+                                                   self.world, b, k, out[0].data_ptr(), out[1].data_ptr(),
+                                                   _stream_ptr(dev)))
+        return out
