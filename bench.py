@@ -247,7 +247,7 @@ def run_b200(args):
 
     B, k, D, K, W = args.batch, args.k, args.dim, args.steps, args.warmup
     # row-range shard of the one global table
-    bounds = [int(round(i * args.rows / world)) for i in range(world + 1)]
+    bounds = pkg.shard_bounds(args.rows, world)
     lo, hi = bounds[rank], bounds[rank + 1]
     ix = build_shard(pkg, lo, hi, D, args.dtype, device)
     esize = 4 if args.dtype == "f32" else 2
@@ -256,17 +256,12 @@ def run_b200(args):
     q_dev = torch.from_numpy(q_host).to(device)
     out_s = torch.empty((B, k), dtype=torch.float32, device=device)
     out_r = torch.empty((B, k), dtype=torch.int64, device=device)
-    if world > 1:
-        g_s = torch.empty((world, B, k), dtype=torch.float32, device=device)
-        g_r = torch.empty((world, B, k), dtype=torch.int64, device=device)
+    sharded = pkg.ShardedIndex(ix) if world > 1 else None
 
     def step(i):
-        s, r = ix.search(q_dev[i], k, out=(out_s, out_r))
         if world > 1:
-            dist.all_gather_into_tensor(g_s, s)
-            dist.all_gather_into_tensor(g_r, r)
-            return pkg.merge_topk(g_s, g_r)
-        return s, r
+            return sharded.search(q_dev[i], k)   # local scan -> one packed all-gather -> K4 merge in place
+        return ix.search(q_dev[i], k, out=(out_s, out_r))
 
     def barrier():
         if world > 1:
@@ -352,17 +347,14 @@ def run_b200(args):
         t0 = time.perf_counter()
         for i in range(W, W + K):
             qd.copy_(pin_q[i], non_blocking=True)
-            s, r = ix.search(qd, k, out=(out_s, out_r))
-            dist.all_gather_into_tensor(g_s, s)
-            dist.all_gather_into_tensor(g_r, r)
-            ms_, mr_ = pkg.merge_topk(g_s, g_r)
+            ms_, mr_ = sharded.search(qd, k)
             hr = mr_.cpu()
             hs = ms_.cpu()
         dt = torch.tensor([(time.perf_counter() - t0) / K], device=device)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": B / float(dt.item()), "unit": "queries/s", "h2d_bytes_per_step": B * D * 4,
                "d2h_bytes_per_step": B * k * 12, "ms_per_step": float(dt.item()) * 1e3,
-               "api": "ResidentIndex.search + all_gather + merge_topk with host query / host result"}
+               "api": "ShardedIndex.search (scan + packed all-gather + merge) with pinned host query in / host result out"}
 
     # optional sweep over other batch sizes (device-resident timing only)
     sweep = []

@@ -563,13 +563,18 @@ inline int umma_plan_stages(int dim, int k, size_t* smem_bytes, bool ts = false)
   return stages;
 }
 
-// K2 wants bf16 rows, dim % 64 == 0, enough rows to fill the grid, and more queries than K1 serves in one pass.
+// Which kernel family serves a batch that shares one row range.  The choice depends on the batch size and the
+// storage type ONLY -- never on the number of rows -- so that a row-range shard of a table takes the same family
+// (same query precision, same per-row arithmetic) as the whole table and sharded results stay bit-identical.
+//   B <= 2  : K1 (fp32 queries, one launch, HBM-bound)      B >= 3, bf16 rows : K2 (bf16 queries on tcgen05)
 inline bool umma_preferred(int dtype, int dim, int B, int k, int64_t nrows) {
-  if (dtype != MMR_BF16 || dim % 64 != 0 || B < 3) return false;  // K1 keeps B <= 2 (fp32 queries, one launch)
-  if (nrows < 64 * 1024 || nrows >= (int64_t(1) << 31)) return false;
+  if (dtype != MMR_BF16 || dim % 64 != 0 || B < 3) return false;
+  if (nrows <= 0 || nrows >= (int64_t(1) << 31)) return false;
   return umma_plan_stages(dim, k, nullptr) >= 2;
 }
+}  // namespace mmr
 
+namespace mmr {
 #ifdef __CUDACC__
 // One K2 search: prep queries -> scan (grid = qtiles x row slots) -> per-query merge.  `ws` is the K2 slice of the
 // workspace (umma_workspace_bytes).  dump != nullptr runs the raw-score debug variant instead of top-k.
