@@ -421,7 +421,7 @@ extern "C" int mmr_search(const mmr_index* ix, const float* queries_dev, const i
   if (uniform) {
 #ifdef MMR_WITH_UMMA
     if (umma_preferred(ix->dtype, ix->dim, B, k, int64_t(ranges[0].second) - ranges[0].first)) {
-      int rc = umma_search(ix->umma, ix->rows, ix->n_rows, ix->dim, ix->sm_count, queries_dev, B, k, ranges[0].first,
+      int rc = umma_search(ix->umma, ix->rows, ix->n_rows, ix->dim, ix->dtype, ix->sm_count, queries_dev, B, k, ranges[0].first,
                            ranges[0].second, ix->row_base, out_scores_dev, out_rows_dev,
                            ws + mmr_search_workspace_bytes(ix, B, k) - umma_workspace_bytes(ix->sm_count, ix->dim, B, k),
                            st, g_err);
@@ -484,11 +484,11 @@ extern "C" int mmr_debug_umma_scores(const mmr_index* ix, const float* queries_d
                                      int64_t row_end, float* out_scores_dev, int64_t out_ld, void* workspace_dev,
                                      size_t workspace_bytes, void* stream) {
   if (!ix || !queries_dev || !out_scores_dev || !workspace_dev) return fail(MMR_ERR_INVALID, "NULL argument");
-  if (ix->dtype != MMR_BF16) return fail(MMR_ERR_UNSUPPORTED, "K2 needs bf16 rows");
+  if (ix->dtype != MMR_BF16 && ix->dtype != MMR_F16) return fail(MMR_ERR_UNSUPPORTED, "K2 needs bf16 or fp16 rows");
   if (B <= 0 || row_begin < 0 || row_end > ix->n_rows || row_end <= row_begin || out_ld < row_end - row_begin)
     return fail(MMR_ERR_INVALID, "bad range");
   if (workspace_bytes < umma_workspace_bytes(ix->sm_count, ix->dim, B, 10)) return fail(MMR_ERR_WORKSPACE, "workspace too small");
-  int rc = umma_search(ix->umma, ix->rows, ix->n_rows, ix->dim, ix->sm_count, queries_dev, B, 10, uint32_t(row_begin),
+  int rc = umma_search(ix->umma, ix->rows, ix->n_rows, ix->dim, ix->dtype, ix->sm_count, queries_dev, B, 10, uint32_t(row_begin),
                        uint32_t(row_end), 0, nullptr, nullptr, static_cast<uint8_t*>(workspace_dev),
                        static_cast<cudaStream_t>(stream), g_err, out_scores_dev, out_ld);
   if (rc == MMR_OK) g_launches += 2;

@@ -24,6 +24,7 @@
 
 #include <cstdlib>
 #include <string>
+#include <type_traits>
 
 #include "common.cuh"
 #include "topk.cuh"
@@ -50,6 +51,7 @@ struct UmmaParams {
   const float* floor; // per query: a proven lower bound of its final k-th best score (nullptr = none)
   float* probe_out;   // probe pass: [n_qtiles * n_rslots][128] best score seen by each CTA (nullptr = real scan)
   int32_t probe_tiles;  // probe pass: row tiles per CTA
+  uint32_t idesc;       // tcgen05 instruction descriptor (bf16 or fp16 operands)
   float* dump;        // DUMP mode: raw scores [B][dump_ld]
   int64_t dump_ld;
 };
@@ -120,9 +122,10 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
   return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) |
          (uint64_t(1) << 46) | (uint64_t(2) << 61);
 }
-// Instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, M=128, N=128.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16_m128_n128() {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(K2_NT >> 3) << 17) | (uint32_t(K2_BM >> 4) << 24);
+// Instruction descriptor, kind::f16: D=f32, A=B=bf16 (format 1) or fp16 (format 0), both K-major, M=128, N=128.
+__host__ __device__ constexpr uint32_t umma_idesc_m128_n128(bool bf16) {
+  return (1u << 4) | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) | (uint32_t(K2_NT >> 3) << 17) |
+         (uint32_t(K2_BM >> 4) << 24);
 }
 
 // Rare path of the epilogue: put `key` into this thread's candidate list (k slots, stride K2_BM in shared
@@ -269,7 +272,7 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     // Warp-uniform loop, one elected lane issues tcgen05.mma and the commits (same lane for both: a commit
     // tracks the MMAs of the thread that executes it).
     const bool leader = elect_one();
-    constexpr uint32_t idesc = umma_idesc_bf16_m128_n128();
+    const uint32_t idesc = p.idesc;
     mbar_wait(bar_q, 0);
     tc_fence_after();
     int stage = 0, acc = 0;
@@ -488,7 +491,8 @@ __global__ void probe_floor_kernel(const float* __restrict__ probe, int n_qtiles
 }
 
 // fp32 queries -> L2-normalised bf16 (LanceDBStore._normalize, then narrowed for the tensor cores). Warp per query.
-__global__ void prep_queries_kernel(const float* __restrict__ q, __nv_bfloat16* __restrict__ out, int B, int dim) {
+template <typename E>
+__global__ void prep_queries_kernel(const float* __restrict__ q, E* __restrict__ out, int B, int dim) {
   const int lane = threadIdx.x & 31;
   const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (qi >= B) return;
@@ -497,7 +501,11 @@ __global__ void prep_queries_kernel(const float* __restrict__ q, __nv_bfloat16* 
   for (int i = lane; i < dim; i += 32) ss = fmaf(s[i], s[i], ss);
   ss = warp_allreduce_sum(ss);
   const float nrm = sqrtf(ss);
-  for (int i = lane; i < dim; i += 32) out[size_t(qi) * dim + i] = __float2bfloat16_rn(nrm > 0.f ? s[i] / nrm : s[i]);
+  for (int i = lane; i < dim; i += 32) {
+    const float x = nrm > 0.f ? s[i] / nrm : s[i];
+    if constexpr (sizeof(E) == 2 && std::is_same<E, __half>::value) out[size_t(qi) * dim + i] = __float2half_rn(x);
+    else out[size_t(qi) * dim + i] = __float2bfloat16_rn(x);
+  }
 }
 #endif  // __CUDACC__
 
@@ -527,14 +535,14 @@ inline mmr_encode_tiled_fn umma_encode_fn() {
 }
 
 // [n_rows, dim] bf16 row-major -> boxes of [128 rows x 64 elements], 128-byte swizzle
-inline bool umma_make_map(CUtensorMap* map, const void* base, int64_t n_rows, int dim) {
+inline bool umma_make_map(CUtensorMap* map, const void* base, int64_t n_rows, int dim, bool bf16 = true) {
   mmr_encode_tiled_fn fn = umma_encode_fn();
   if (!fn) return false;
   cuuint64_t gdim[2] = {cuuint64_t(dim), cuuint64_t(n_rows)};
   cuuint64_t gstr[1] = {cuuint64_t(dim) * 2};
   cuuint32_t box[2] = {64, 128};
   cuuint32_t estr[2] = {1, 1};
-  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+  return fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -566,9 +574,9 @@ inline int umma_plan_stages(int dim, int k, size_t* smem_bytes, bool ts = false)
 // Which kernel family serves a batch that shares one row range.  The choice depends on the batch size and the
 // storage type ONLY -- never on the number of rows -- so that a row-range shard of a table takes the same family
 // (same query precision, same per-row arithmetic) as the whole table and sharded results stay bit-identical.
-//   B <= 2  : K1 (fp32 queries, one launch, HBM-bound)      B >= 3, bf16 rows : K2 (bf16 queries on tcgen05)
+//   B <= 2  : K1 (fp32 queries, one launch, HBM-bound)      B >= 3, bf16/fp16 rows : K2 (16-bit queries on tcgen05)
 inline bool umma_preferred(int dtype, int dim, int B, int k, int64_t nrows) {
-  if (dtype != MMR_BF16 || dim % 64 != 0 || B < 3) return false;
+  if ((dtype != MMR_BF16 && dtype != MMR_F16) || dim % 64 != 0 || B < 3) return false;
   if (nrows <= 0 || nrows >= (int64_t(1) << 31)) return false;
   return umma_plan_stages(dim, k, nullptr) >= 2;
 }
@@ -578,12 +586,12 @@ namespace mmr {
 #ifdef __CUDACC__
 // One K2 search: prep queries -> scan (grid = qtiles x row slots) -> per-query merge.  `ws` is the K2 slice of the
 // workspace (umma_workspace_bytes).  dump != nullptr runs the raw-score debug variant instead of top-k.
-inline int umma_search(UmmaIndexState& st, const void* rows, int64_t n_rows, int dim, int sm_count,
+inline int umma_search(UmmaIndexState& st, const void* rows, int64_t n_rows, int dim, int dtype, int sm_count,
                        const float* queries, int B, int k, uint32_t r0, uint32_t r1, int64_t row_base, float* out_s,
                        int64_t* out_r, uint8_t* ws, cudaStream_t stream, std::string& err, float* dump = nullptr,
                        int64_t dump_ld = 0) {
   if (!st.valid || st.rows != rows || st.n_rows != n_rows) {
-    if (!umma_make_map(&st.map, rows, n_rows, dim)) {
+    if (!umma_make_map(&st.map, rows, n_rows, dim, dtype == MMR_BF16)) {
       err = "cuTensorMapEncodeTiled failed for the index";
       return MMR_ERR_CUDA;
     }
@@ -620,17 +628,19 @@ inline int umma_search(UmmaIndexState& st, const void* rows, int64_t n_rows, int
   float* probe = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(partial) + umma_align(size_t(ctas_max) * K2_BM * k * 8));
   float* floor = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(probe) + umma_align(size_t(ctas_max) * K2_BM * 4));
   const char* noprobe = getenv("MMR_UMMA_NOPROBE");
-  prep_queries_kernel<<<(B + 3) / 4, 128, 0, stream>>>(queries, qb, B, dim);
+  if (dtype == MMR_BF16) prep_queries_kernel<__nv_bfloat16><<<(B + 3) / 4, 128, 0, stream>>>(queries, qb, B, dim);
+  else prep_queries_kernel<__half><<<(B + 3) / 4, 128, 0, stream>>>(queries, reinterpret_cast<__half*>(qb), B, dim);
   const int max_q_per_pass = sm_count * K2_BM;
   for (int q0 = 0; q0 < B; q0 += max_q_per_pass) {
     const int bq = std::min(B - q0, max_q_per_pass);
     CUtensorMap tm_q;
-    if (!umma_make_map(&tm_q, qb + size_t(q0) * dim, bq, dim)) {
+    if (!umma_make_map(&tm_q, qb + size_t(q0) * dim, bq, dim, dtype == MMR_BF16)) {
       err = "cuTensorMapEncodeTiled failed for the queries";
       return MMR_ERR_CUDA;
     }
     UmmaParams p{};
     p.ks = dim / 64;
+    p.idesc = umma_idesc_m128_n128(dtype == MMR_BF16);
     p.nstages = stages;
     p.k = k;
     p.B = bq;
@@ -646,10 +656,10 @@ inline int umma_search(UmmaIndexState& st, const void* rows, int64_t n_rows, int
     const int grid = p.n_qtiles * p.n_rslots;
     // probe pass: worth it when every CTA streams many tiles (the warm-up it removes is ~k ln(n/k) inserts/thread)
     const int64_t tiles_per_cta = ntiles / p.n_rslots;
-    if (!dump && !(noprobe && noprobe[0] == '1') && tiles_per_cta >= 64 && p.n_rslots >= k) {
+    if (!dump && !(noprobe && noprobe[0] == '1') && tiles_per_cta >= 8 && p.n_rslots >= k) {
       UmmaParams pp = p;
       pp.probe_out = probe;
-      pp.probe_tiles = int(std::max<int64_t>(2, std::min<int64_t>(16, tiles_per_cta / 32)));
+      pp.probe_tiles = int(std::max<int64_t>(1, std::min<int64_t>(16, tiles_per_cta / 24)));
       if (ts) scan_umma_kernel<false, true><<<grid, K2_THREADS, smem_bytes, stream>>>(tm_q, st.map, pp);
       else scan_umma_kernel<false, false><<<grid, K2_THREADS, smem_bytes, stream>>>(tm_q, st.map, pp);
       const int wpb = 4;

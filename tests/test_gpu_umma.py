@@ -94,3 +94,19 @@ def test_k2_equals_k1_on_segments_and_ties(mmr):
     overlap = np.mean([len(set(a.tolist()) & set(b.tolist())) / 12 for a, b in zip(r1.cpu().numpy(), r2.cpu().numpy())])
     assert overlap > 0.9
     ix.close()
+
+
+def test_fp16_rows_on_tensor_cores(mmr):
+    """fp16 storage takes the same tcgen05 path (operand format switch in the instruction descriptor)."""
+    rows = util.unit_rows(90_000, 512, seed=93)
+    ix = mmr.ResidentIndex.from_f32(rows, dtype="f16")
+    stored = ix.rows.float()
+    q = util.queries(7, 512)
+    qn = torch.from_numpy(np.stack([np.asarray(ofs.normalize(v), np.float32) for v in q])).cuda().half().float()
+    got = ix.debug_umma_scores(torch.from_numpy(q).cuda(), 0, 90_000)
+    assert (got - qn @ stored.T).abs().max().item() < 3e-6
+    s, r = ix.search(torch.from_numpy(q).cuda(), 10)
+    assert mmr._native.lib().mmr_last_kernel() == 2
+    for j in range(7):
+        util.check_topk(s[j].cpu().numpy(), r[j].cpu().numpy(), util.oracle_scores(rows, q[j]), 10, util.TOL_BF16, what=f"f16 q{j}")
+    ix.close()
