@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f16", "f32"])
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "nccl"],
+                    help="N>1: fused = peer-memory stores from the scan kernel + wait/merge kernel; nccl = all-gather + merge")
     ap.add_argument("--sweep", default="8,128,1024", help="extra batch sizes reported under 'sweep' (N=1 only)")
     return ap.parse_args()
 
@@ -256,7 +258,7 @@ def run_b200(args):
     q_dev = torch.from_numpy(q_host).to(device)
     out_s = torch.empty((B, k), dtype=torch.float32, device=device)
     out_r = torch.empty((B, k), dtype=torch.int64, device=device)
-    sharded = pkg.ShardedIndex(ix) if world > 1 else None
+    sharded = pkg.ShardedIndex(ix, exchange=args.exchange) if world > 1 else None
 
     def step(i):
         if world > 1:
@@ -394,7 +396,9 @@ def run_b200(args):
             "value": qps, "unit": "queries/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"{args.rows}x{D} {args.dtype} unit-norm rows, top-{k}, query batch {B}",
-                       "parallelism": f"row-range shards x{world}" + (", NCCL all-gather + merge kernel" if world > 1 else ""),
+                       "parallelism": f"row-range shards x{world}" + (
+                           "" if world == 1 else (", NCCL all-gather + merge kernel" if sharded.exchange == "nccl" else
+                                                  ", fused exchange: scan kernel stores results into peers over NVLink + wait/merge kernel")),
                        "l2": "index (>= 1.28 GB per GPU) is larger than L2 (126 MB); no flush needed",
                        "rows_per_gpu": hi - lo},
             "hbm_GBs_aggregate": args.rows * D * esize / (ms_step * 1e-3) / 1e9,

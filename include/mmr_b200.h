@@ -114,6 +114,23 @@ int mmr_merge_topk_strided(const float* scores_dev, const int64_t* rows_dev, int
                            int64_t* out_rows_dev, void* stream);
 
 /*
+ * Fused scan + exchange for row-range shards on one NVLink/NVSwitch box (replaces scan -> NCCL all-gather -> merge).
+ * Every rank owns a symmetric buffer of mmr_exchange_buffer_bytes(G, B, k) bytes, ZEROED once, mapped into every
+ * process (e.g. torch.distributed._symmetric_memory); peer_bufs_host[g] is rank g's buffer address as mapped in THIS
+ * process.  Per search: the shard scan writes its [B, k] result straight into every peer's buffer with peer-mapped
+ * stores and releases a flag (for B <= 2 inside the scan kernel's last CTA; otherwise a small push kernel), then a
+ * wait+merge kernel acquires the G flags and merges the G lists.  seq = 1, 2, 3, ... identical on all ranks.
+ * The answer equals mmr_search + all-gather + mmr_merge_topk bit for bit.  A peer that never arrives makes the merge
+ * give up after 5 s and write row id -2 into out_rows[q * k] instead of hanging the GPU.
+ */
+size_t mmr_exchange_buffer_bytes(int32_t G, int32_t B, int32_t k);
+size_t mmr_search_exchange_workspace_bytes(const mmr_index* index, int32_t B, int32_t k);
+int mmr_search_exchange(const mmr_index* index, const float* queries_dev, const int32_t* query_seg_host, int32_t B,
+                        int32_t k, const uint64_t* peer_bufs_host, int32_t G, int32_t rank, uint32_t seq,
+                        float* out_scores_dev, int64_t* out_rows_dev, void* workspace_dev, size_t workspace_bytes,
+                        void* stream);
+
+/*
  * Fusion + gate (K5): _fuse_results with no rerank scores (reference app/ml/retrieve.py:158-195) and
  * _confidence_low (app/ml/generate.py:56-60), bit-identical float64 results.
  *   text_* [B, kt], img_* [B, ki] as written by mmr_search (either may be NULL with k = 0).

@@ -92,6 +92,107 @@ __global__ void merge_shards_kernel(const float* __restrict__ scores, const int6
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused exchange over peer memory (replaces the NCCL all-gather of the tiny per-shard results).
+// Every rank owns one symmetric buffer, identical layout everywhere:
+//   [0, 256)                       flags  u32 [2 parities][MMR_XCHG_MAX_PEERS]   (sequence numbers, start at 0)
+//   [256, ...)                     slots  [2 parities][G source ranks][wire_bytes], wire = scores f32 [B*k] | rows i64 [B*k]
+// push_wire_kernel   : CTA g copies this rank's wire into peer g's slot [parity][rank] with peer-mapped stores, fences at
+//                      system scope and releases peer g's flag [parity][rank] = seq.  (K1 does this itself in its last CTA.)
+// merge_wait_kernel  : one warp per query; lane g acquires flag [parity][g] >= seq (bounded spin), then the warp merges the
+//                      G x k candidates out of the local slots (written by the peers) -- K4 fused with the wait.
+// Two parities are enough: a rank cannot start search seq+2 before every peer finished merging search seq.
+// ------------------------------------------------------------------------------------------------
+constexpr int MMR_XCHG_MAX_PEERS = 16;
+constexpr int MMR_XCHG_HEADER = 256;
+
+struct PeerPtrs {
+  uint64_t slot[MMR_XCHG_MAX_PEERS];  // this rank's slot inside peer g's buffer
+  uint64_t flag[MMR_XCHG_MAX_PEERS];  // this rank's flag inside peer g's buffer
+};
+
+__global__ void push_wire_kernel(const uint8_t* __restrict__ wire, uint32_t wire_bytes, const PeerPtrs peers, uint32_t seq) {
+  const int g = blockIdx.x;
+  const uint64_t* peer_slot = peers.slot;
+  const uint64_t* peer_flag = peers.flag;
+  const uint4* src = reinterpret_cast<const uint4*>(wire);
+  uint4* dst = reinterpret_cast<uint4*>(peer_slot[g]);
+  const uint32_t n16 = wire_bytes / 16;
+  for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+  for (uint32_t i = n16 * 16 + threadIdx.x; i < wire_bytes; i += blockDim.x)
+    reinterpret_cast<uint8_t*>(peer_slot[g])[i] = wire[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flag[g]), "r"(seq) : "memory");
+}
+
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <int KPL>
+__global__ void merge_wait_kernel(const uint8_t* __restrict__ xbuf, int parity, uint32_t seq, uint32_t wire_bytes,
+                                  uint32_t score_bytes, int G, int B, int k, float* __restrict__ out_scores,
+                                  int64_t* __restrict__ out_rows, uint64_t timeout_ns) {
+  const int lane = threadIdx.x & 31;
+  const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (qi >= B) return;
+  const uint32_t* flags = reinterpret_cast<const uint32_t*>(xbuf) + parity * MMR_XCHG_MAX_PEERS;
+  bool ok = true;
+  if (lane < G) {
+    const uint64_t t0 = globaltimer_ns();
+    while (ld_acquire_sys_u32(flags + lane) < seq) {
+      if (globaltimer_ns() - t0 > timeout_ns) {  // a peer died: do not hang the GPU, report instead
+        ok = false;
+        break;
+      }
+    }
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  if (!ok) {
+    if (lane == 0) {
+      out_rows[size_t(qi) * k] = -2;  // MMR exchange timeout marker
+      out_scores[size_t(qi) * k] = -INFINITY;
+    }
+    return;
+  }
+  const uint8_t* slots = xbuf + MMR_XCHG_HEADER + size_t(parity) * G * wire_bytes;
+  WarpTopK<KPL> m;
+  m.clear();
+  uint64_t thr = 0ull;
+  const int total = G * k;
+  for (int i0 = 0; i0 < total; i0 += 32) {
+    const int i = i0 + lane;
+    bool valid = i < total;
+    uint64_t key = 0ull;
+    if (valid) {
+      const int g = i / k, j = i % k;
+      const uint8_t* slot = slots + size_t(g) * wire_bytes;
+      const size_t o = size_t(qi) * k + j;
+      const long long r = __ldcg(reinterpret_cast<const long long*>(slot + score_bytes) + o);  // L2: written by peers
+      valid = r >= 0;
+      if (valid) key = make_key(__ldcg(reinterpret_cast<const float*>(slot) + o), uint32_t(r));
+    }
+    thr = m.offer(key, valid, thr, k, lane);
+  }
+#pragma unroll
+  for (int j = 0; j < KPL; ++j) {
+    const int pos = j * 32 + lane;
+    if (pos < k) {
+      const uint64_t key = m.key[j];
+      out_scores[size_t(qi) * k + pos] = key ? key_score(key) : -INFINITY;
+      out_rows[size_t(qi) * k + pos] = key ? int64_t(key_row(key)) : int64_t(-1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K5 -- text+image score fusion and the CONFIDENCE_TAU gate for the rerank-off path.
 // Follows _z_scores / _fuse_results (reference app/ml/retrieve.py:186-195, 158-183) and _confidence_low
 // (app/ml/generate.py:56-60) operation by operation so the result is bit-identical to the reference:

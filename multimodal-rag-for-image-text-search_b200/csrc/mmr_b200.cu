@@ -301,8 +301,17 @@ extern "C" size_t mmr_search_workspace_bytes(const mmr_index* ix, int32_t B, int
   return total;
 }
 
+struct ExchangeInfo {  // fused push by K1's last CTA (only when one launch covers all B queries)
+  int n_peers = 0;
+  uint32_t seq = 0;
+  uint32_t wire_score_bytes = 0;
+  uint64_t slot[MMR_MAX_PEERS] = {};
+  uint64_t flag[MMR_MAX_PEERS] = {};
+};
+
 static int search_uniform_stream(const mmr_index* ix, const float* q, int B, int k, uint32_t r0, uint32_t r1,
-                                 float* out_s, int64_t* out_r, uint8_t* ws, cudaStream_t st) {
+                                 float* out_s, int64_t* out_r, uint8_t* ws, cudaStream_t st,
+                                 const ExchangeInfo* xi = nullptr) {
   const int kpl = k <= 32 ? 1 : 2;
   const int R = rows_per_stage(ix->dtype);
   const int64_t nchunks = (int64_t(r1) - r0 + R - 1) / R;
@@ -325,6 +334,15 @@ static int search_uniform_stream(const mmr_index* ix, const float* q, int B, int
     p.row_base = ix->row_base;
     p.items = nullptr;
     p.n_items = 0;
+    if (xi && B <= 4) {
+      p.n_peers = xi->n_peers;
+      p.seq = xi->seq;
+      p.wire_score_bytes = xi->wire_score_bytes;
+      for (int g = 0; g < xi->n_peers; ++g) {
+        p.peer_slot[g] = xi->slot[g];
+        p.peer_flag[g] = xi->flag[g];
+      }
+    }
     int rc = launch_stream(ix, p, nq_pad, kpl, grid, st);
     if (rc != MMR_OK) return rc;
   }
@@ -475,6 +493,94 @@ extern "C" int mmr_search_host(mmr_index* ix, const float* queries_host, const i
   CUDA_TRY(cudaStreamSynchronize(st));
   memcpy(out_scores_host, ix->h_scores, size_t(B) * k * 4);
   memcpy(out_rows_host, ix->h_rows, size_t(B) * k * 8);
+  return MMR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ fused exchange
+static uint32_t xchg_score_bytes(int B, int k) { return uint32_t((size_t(B) * k * 4 + 7) / 8 * 8); }
+static uint32_t xchg_wire_bytes(int B, int k) { return uint32_t((xchg_score_bytes(B, k) + size_t(B) * k * 8 + 15) / 16 * 16); }
+
+extern "C" size_t mmr_exchange_buffer_bytes(int32_t G, int32_t B, int32_t k) {
+  if (G <= 0 || G > MMR_XCHG_MAX_PEERS || B <= 0 || k <= 0) return 0;
+  return size_t(MMR_XCHG_HEADER) + size_t(2) * G * xchg_wire_bytes(B, k);
+}
+
+extern "C" size_t mmr_search_exchange_workspace_bytes(const mmr_index* ix, int32_t B, int32_t k) {
+  const size_t base = mmr_search_workspace_bytes(ix, B, k);
+  return base ? base + align_up(xchg_wire_bytes(B, std::min<int32_t>(k, MMR_MAX_K)), 256) : 0;
+}
+
+extern "C" int mmr_search_exchange(const mmr_index* ix, const float* queries_dev, const int32_t* query_seg_host,
+                                   int32_t B, int32_t k, const uint64_t* peer_bufs_host, int32_t G, int32_t rank,
+                                   uint32_t seq, float* out_scores_dev, int64_t* out_rows_dev, void* workspace_dev,
+                                   size_t workspace_bytes, void* stream) {
+  if (!ix) return fail(MMR_ERR_INVALID, "index is NULL");
+  if (!peer_bufs_host || G < 1 || G > MMR_XCHG_MAX_PEERS || rank < 0 || rank >= G)
+    return fail(MMR_ERR_INVALID, "bad peer table (G=%d, rank=%d)", G, rank);
+  if (seq == 0) return fail(MMR_ERR_INVALID, "seq must start at 1 and grow by 1 per search");
+  if (B <= 0 || k < 1 || k > MMR_MAX_K) return fail(MMR_ERR_INVALID, "bad B or k");
+  if (!queries_dev || !out_scores_dev || !out_rows_dev || !workspace_dev) return fail(MMR_ERR_INVALID, "NULL buffer");
+  const size_t base_ws = mmr_search_workspace_bytes(ix, B, k);
+  if (workspace_bytes < mmr_search_exchange_workspace_bytes(ix, B, k)) return fail(MMR_ERR_WORKSPACE, "workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
+  const uint32_t score_bytes = xchg_score_bytes(B, k), wire_bytes = xchg_wire_bytes(B, k);
+  const int parity = int(seq & 1u);
+  uint8_t* wire = ws + base_ws;  // this rank's own result, [scores | rows]
+  float* w_scores = reinterpret_cast<float*>(wire);
+  int64_t* w_rows = reinterpret_cast<int64_t*>(wire + score_bytes);
+  ExchangeInfo xi;
+  xi.n_peers = G;
+  xi.seq = seq;
+  xi.wire_score_bytes = score_bytes;
+  for (int g = 0; g < G; ++g) {
+    xi.slot[g] = peer_bufs_host[g] + MMR_XCHG_HEADER + (size_t(parity) * G + rank) * wire_bytes;
+    xi.flag[g] = peer_bufs_host[g] + (size_t(parity) * MMR_XCHG_MAX_PEERS + rank) * 4;
+  }
+  // 1. the shard-local scan
+  bool pushed = false;
+  const int nseg = int(ix->seg.size()) - 1;
+  bool uniform = true;
+  int s0 = query_seg_host ? query_seg_host[0] : -1;
+  for (int b = 0; b < B && uniform; ++b) uniform = (query_seg_host ? query_seg_host[b] : -1) == s0;
+  if (s0 < -1 || s0 >= nseg) return fail(MMR_ERR_INVALID, "segment %d out of range", s0);
+  const uint32_t r0 = s0 < 0 ? 0u : uint32_t(ix->seg[s0]);
+  const uint32_t r1 = s0 < 0 ? uint32_t(ix->n_rows) : uint32_t(ix->seg[s0 + 1]);
+  bool k2 = false;
+#ifdef MMR_WITH_UMMA
+  k2 = uniform && umma_preferred(ix->dtype, ix->dim, B, k, int64_t(r1) - r0);
+#endif
+  if (uniform && !k2 && B <= 4) {
+    // K1 computes and pushes in ONE kernel: its last CTA stores the result into every peer over NVLink
+    int rc = search_uniform_stream(ix, queries_dev, B, k, r0, r1, w_scores, w_rows, ws, st, &xi);
+    if (rc != MMR_OK) return rc;
+    pushed = true;
+  } else {
+    int rc = mmr_search(ix, queries_dev, query_seg_host, B, k, w_scores, w_rows, ws, base_ws, st);
+    if (rc != MMR_OK) return rc;
+  }
+  // 2. push (when the scan kernel did not do it itself)
+  if (!pushed) {
+    PeerPtrs pp;
+    for (int g = 0; g < MMR_XCHG_MAX_PEERS; ++g) {
+      pp.slot[g] = g < G ? xi.slot[g] : 0;
+      pp.flag[g] = g < G ? xi.flag[g] : 0;
+    }
+    push_wire_kernel<<<G, 256, 0, st>>>(wire, wire_bytes, pp, seq);
+    g_launches++;
+  }
+  // 3. wait for every peer's slot, merge in place
+  const uint8_t* local = reinterpret_cast<const uint8_t*>(peer_bufs_host[rank]);
+  const int wpb = 4;
+  const uint64_t timeout_ns = 5000000000ull;
+  if (k <= 32)
+    merge_wait_kernel<1><<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(local, parity, seq, wire_bytes, score_bytes, G, B, k,
+                                                                 out_scores_dev, out_rows_dev, timeout_ns);
+  else
+    merge_wait_kernel<2><<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(local, parity, seq, wire_bytes, score_bytes, G, B, k,
+                                                                 out_scores_dev, out_rows_dev, timeout_ns);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
   return MMR_OK;
 }
 

@@ -28,6 +28,7 @@ namespace mmr {
 constexpr int K1_NW = 8;           // consumer warps per CTA
 constexpr int K1_THREADS = K1_NW * 32;
 constexpr int K1_SMEM_BUDGET = 200 * 1024;
+constexpr int MMR_MAX_PEERS = 16;
 
 struct ScanItem {  // varlen mode: one contiguous row range of one query (rows are index-local ordinals)
   uint32_t row_begin;
@@ -50,6 +51,13 @@ struct StreamParams {
   int64_t row_base;             // shard base added to the int64 row ids written out
   const ScanItem* items;        // varlen mode (nullptr = uniform)
   int32_t n_items;
+  // Fused exchange (row-range shards over NVLink): the last CTA also stores the final [B, k] result straight into
+  // every peer's symmetric buffer (this rank's slot) and then releases that peer's flag with `seq`.
+  int32_t n_peers;              // 0 = no exchange
+  uint32_t seq;
+  uint32_t wire_score_bytes;    // offset of the int64 rows inside one wire slot
+  uint64_t peer_slot[MMR_MAX_PEERS];  // address of this rank's slot inside peer g's buffer (peer-mapped)
+  uint64_t peer_flag[MMR_MAX_PEERS];  // address of this rank's flag inside peer g's buffer
 };
 
 template <typename E>
@@ -334,11 +342,23 @@ __global__ void __launch_bounds__(K1_THREADS, 1) scan_stream_kernel(const Stream
           if (pos < k) {
             const uint64_t key = f.key[j];
             const size_t o = size_t(p.q_first + qi) * k + pos;
-            p.out_scores[o] = key ? key_score(key) : -INFINITY;
-            p.out_rows[o] = key ? int64_t(key_row(key)) + p.row_base : int64_t(-1);
+            const float sc = key ? key_score(key) : -INFINITY;
+            const int64_t rw = key ? int64_t(key_row(key)) + p.row_base : int64_t(-1);
+            p.out_scores[o] = sc;
+            p.out_rows[o] = rw;
+            for (int g = 0; g < p.n_peers; ++g) {  // peer-mapped stores over NVLink (or local for g == rank)
+              reinterpret_cast<float*>(p.peer_slot[g])[o] = sc;
+              reinterpret_cast<int64_t*>(p.peer_slot[g] + p.wire_score_bytes)[o] = rw;
+            }
           }
         }
       }
+    }
+    if (p.n_peers > 0) {
+      __threadfence_system();
+      __syncthreads();
+      if (int(threadIdx.x) < p.n_peers)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.peer_flag[threadIdx.x]), "r"(p.seq) : "memory");
     }
     if (threadIdx.x == 0) *p.ticket = 0u;  // ready for the next launch
   } else {

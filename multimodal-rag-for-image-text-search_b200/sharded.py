@@ -84,16 +84,83 @@ def merge_gathered_numpy(gathered: GatheredWire) -> Tuple[np.ndarray, np.ndarray
     return out_s, out_r
 
 
-class ShardedIndex:
-    """This rank's shard + the exchange.  `local` is a ResidentIndex built with row_base = bounds[rank]."""
+class PeerExchange:
+    """Symmetric buffers for the fused exchange (mmr_search_exchange): one buffer per rank, mapped into every
+    process with torch's symmetric memory (CUDA VMM handles over the process-group store; NVLink peer access).
+    `ptrs[g]` = rank g's buffer as addressed from this process."""
 
-    def __init__(self, local, group=None) -> None:
+    def __init__(self, world: int, rank: int, b: int, k: int, device, group=None) -> None:
+        import torch.distributed._symmetric_memory as symm
+        from . import _native as N
+
+        self.b, self.k = b, k
+        nbytes = int(N.lib().mmr_exchange_buffer_bytes(world, b, k))
+        self.buf = symm.empty(nbytes, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        grp = group if group is not None else dist.group.WORLD
+        try:
+            self.handle = symm.rendezvous(self.buf, grp)
+        except Exception:
+            symm.enable_symm_mem_for_group(grp.group_name)
+            self.handle = symm.rendezvous(self.buf, grp.group_name)
+        self.ptrs = np.ascontiguousarray([int(p) for p in self.handle.buffer_ptrs], dtype=np.uint64)
+        assert len(self.ptrs) == world and int(self.ptrs[rank]) == self.buf.data_ptr()
+        self.seq = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)          # every buffer is zeroed before anybody pushes into it
+
+
+class ShardedIndex:
+    """This rank's shard + the exchange.  `local` is a ResidentIndex built with row_base = bounds[rank].
+
+    exchange = "fused": scan kernels store their result straight into every peer's symmetric buffer over NVLink and
+                        a wait+merge kernel finishes (no NCCL on the data path);
+               "nccl" : scan -> one packed all-gather -> K4 merge (correctness baseline, any backend);
+               "auto" : fused when the symmetric-memory rendezvous works, else nccl.
+    """
+
+    def __init__(self, local, group=None, exchange: str = "auto") -> None:
         self.local = local
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.exchange = exchange
         self._wire: Optional[Wire] = None
         self._gathered: Optional[GatheredWire] = None
         self._out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+        self._peer: Optional[PeerExchange] = None
+        self._ws: Optional[torch.Tensor] = None
+
+    def _peer_exchange(self, b: int, k: int) -> Optional[PeerExchange]:
+        if self.exchange == "nccl" or self.world == 1:
+            return None
+        if self._peer is None or (self._peer.b, self._peer.k) != (b, k):
+            try:
+                self._peer = PeerExchange(self.world, self.rank, b, k, self.local.device, self.group)
+            except Exception:
+                if self.exchange == "fused":
+                    raise
+                self.exchange = "nccl"     # symmetric memory unavailable: every rank fails the same way
+                return None
+        return self._peer
+
+    def _search_fused(self, peer: PeerExchange, queries: torch.Tensor, b: int, k: int, segments, out):
+        from . import _native as N
+        from .index import _stream_ptr
+
+        lib = N.lib()
+        ix = self.local
+        need = int(lib.mmr_search_exchange_workspace_bytes(ix._handle, b, k))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.zeros(need, dtype=torch.uint8, device=ix.device)
+        seg_arr = None if segments is None else np.ascontiguousarray(segments, dtype=np.int32)
+        peer.seq += 1
+        with torch.cuda.device(ix.device):
+            N.check(lib.mmr_search_exchange(ix._handle, queries.data_ptr(), None if seg_arr is None else seg_arr.ctypes.data,
+                                            b, k, peer.ptrs.ctypes.data, self.world, self.rank, peer.seq,
+                                            out[0].data_ptr(), out[1].data_ptr(), self._ws.data_ptr(), self._ws.numel(),
+                                            _stream_ptr(ix.device)))
+        return out
 
     def _buffers(self, b: int, k: int):
         if self._wire is None or (self._wire.b, self._wire.k) != (b, k):
@@ -109,9 +176,14 @@ class ShardedIndex:
         from . import _native as N
         from .index import _stream_ptr
 
-        b = int(queries.shape[0]) if queries.dim() == 2 else 1
+        if queries.dim() == 1:
+            queries = queries[None, :]
+        b = int(queries.shape[0])
         k = max(int(k), 1)
         wire, gathered, out = self._buffers(b, k)
+        peer = self._peer_exchange(b, k)
+        if peer is not None:
+            return self._search_fused(peer, queries, b, k, segments, out)
         self.local.search(queries, k, segments, out=(wire.scores, wire.rows))
         if self.world == 1:
             return wire.scores, wire.rows
