@@ -95,6 +95,15 @@ int mmr_search(const mmr_index* index, const float* queries_dev, const int32_t* 
                int32_t k, float* out_scores_dev, int64_t* out_rows_dev, void* workspace_dev, size_t workspace_bytes,
                void* stream);
 /*
+ * Same scan with explicit row ranges per query instead of one segment id: query b scans
+ * ranges_host[2*r], ranges_host[2*r+1]) for r in [range_off_host[b], range_off_host[b+1]).  This is how a store that
+ * appends delta segments between compactions (upsert = tombstone + append, lancedb_store.py:87-101) searches a tenant
+ * that currently owns several ranges.  Rows overwritten with NaN (tombstones) never appear in results.
+ */
+int mmr_search_ranges(const mmr_index* index, const float* queries_dev, int32_t B, int32_t k,
+                      const int32_t* range_off_host, const int64_t* ranges_host, float* out_scores_dev,
+                      int64_t* out_rows_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+/*
  * Same with HOST buffers: copies the queries in, scans, copies results out and synchronises the stream.
  * This is the call B200Store.search_* makes per request; its time is the end-to-end figure in bench.py.
  */

@@ -25,6 +25,7 @@ SYMBOLS = [
     ("mmr_load_rows_f32_host", C.c_int, [C.c_int, _p, _p, C.c_int, _i64, C.c_int, C.c_int, _p]),
     ("mmr_search_workspace_bytes", _sz, [_p, _i32, _i32]),
     ("mmr_search", C.c_int, [_p, _p, _p, _i32, _i32, _p, _p, _p, _sz, _p]),
+    ("mmr_search_ranges", C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _p, _p, _sz, _p]),
     ("mmr_search_host", C.c_int, [_p, _p, _p, _i32, _i32, _p, _p, _p]),
     ("mmr_merge_topk", C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),
     ("mmr_merge_topk_strided", C.c_int, [_p, _p, _i64, _i64, _i32, _i32, _i32, _p, _p, _p]),

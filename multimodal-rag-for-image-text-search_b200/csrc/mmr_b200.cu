@@ -350,13 +350,16 @@ static int search_uniform_stream(const mmr_index* ix, const float* q, int B, int
   return MMR_OK;
 }
 
-static int search_varlen_stream(const mmr_index* ix, const float* q, const std::vector<std::pair<uint32_t, uint32_t>>& ranges,
-                                int k, float* out_s, int64_t* out_r, uint8_t* ws, size_t ws_bytes, cudaStream_t st) {
+// `ranges[b]` = the row ranges query b scans (a tenant is one base segment plus any appended delta segments).
+static int search_varlen_stream(const mmr_index* ix, const float* q,
+                                const std::vector<std::vector<std::pair<uint32_t, uint32_t>>>& ranges, int k, float* out_s,
+                                int64_t* out_r, uint8_t* ws, size_t ws_bytes, cudaStream_t st) {
   const int B = int(ranges.size());
   const int kpl = k <= 32 ? 1 : 2;
   const int R = rows_per_stage(ix->dtype);
   int64_t total_rows = 0;
-  for (auto& r : ranges) total_rows += int64_t(r.second) - r.first;
+  for (auto& rq : ranges)
+    for (auto& r : rq) total_rows += int64_t(r.second) - r.first;
   const int twarps = ix->sm_count * K1_NW;
   const int64_t target = int64_t(twarps) * VARLEN_ITEMS_PER_WARP;
   int64_t item_rows = std::max<int64_t>(64, (total_rows + target - 1) / target);
@@ -365,18 +368,20 @@ static int search_varlen_stream(const mmr_index* ix, const float* q, const std::
   std::vector<int32_t> off(B + 1, 0);
   for (int b = 0; b < B; ++b) {
     off[b] = int32_t(items.size());
-    for (int64_t s = ranges[b].first; s < int64_t(ranges[b].second); s += item_rows) {
-      ScanItem it;
-      it.row_begin = uint32_t(s);
-      it.row_end = uint32_t(std::min<int64_t>(s + item_rows, ranges[b].second));
-      it.query = b;
-      it.pad = 0;
-      items.push_back(it);
+    for (auto& r : ranges[b]) {
+      for (int64_t s = r.first; s < int64_t(r.second); s += item_rows) {
+        ScanItem it;
+        it.row_begin = uint32_t(s);
+        it.row_end = uint32_t(std::min<int64_t>(s + item_rows, r.second));
+        it.query = b;
+        it.pad = 0;
+        items.push_back(it);
+      }
     }
   }
   off[B] = int32_t(items.size());
   const int n_items = int(items.size());
-  if (n_items > max_varlen_items(ix, B)) return fail(MMR_ERR_WORKSPACE, "varlen plan produced %d items", n_items);
+  if (n_items > max_varlen_items(ix, B)) return fail(MMR_ERR_WORKSPACE, "varlen plan produced %d items (too many row ranges)", n_items);
   const size_t part_bytes = align_up(size_t(std::max(n_items, 1)) * k * 8, 256);
   const size_t item_bytes = align_up(size_t(std::max(n_items, 1)) * sizeof(ScanItem), 256);
   const size_t off_bytes = align_up(size_t(B + 1) * 4, 256);
@@ -453,7 +458,53 @@ extern "C" int mmr_search(const mmr_index* ix, const float* queries_dev, const i
     return search_uniform_stream(ix, queries_dev, B, k, ranges[0].first, ranges[0].second, out_scores_dev,
                                  out_rows_dev, ws, st);
   }
-  return search_varlen_stream(ix, queries_dev, ranges, k, out_scores_dev, out_rows_dev, ws, workspace_bytes, st);
+  std::vector<std::vector<std::pair<uint32_t, uint32_t>>> per_query(B);
+  for (int b = 0; b < B; ++b) per_query[b].push_back(ranges[b]);
+  return search_varlen_stream(ix, queries_dev, per_query, k, out_scores_dev, out_rows_dev, ws, workspace_bytes, st);
+}
+
+// Explicit row ranges per query: query b scans ranges[range_off[b] .. range_off[b+1]) (pairs of [begin, end) row
+// ordinals).  Used by stores that append delta segments between compactions.
+extern "C" int mmr_search_ranges(const mmr_index* ix, const float* queries_dev, int32_t B, int32_t k,
+                                 const int32_t* range_off_host, const int64_t* ranges_host, float* out_scores_dev,
+                                 int64_t* out_rows_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  if (!ix) return fail(MMR_ERR_INVALID, "index is NULL");
+  if (B <= 0) return fail(MMR_ERR_INVALID, "B must be >= 1");
+  if (k < 1 || k > MMR_MAX_K) return fail(MMR_ERR_INVALID, "k must be in [1, %d]", MMR_MAX_K);
+  if (!queries_dev || !range_off_host || !out_scores_dev || !out_rows_dev || !workspace_dev)
+    return fail(MMR_ERR_INVALID, "NULL buffer");
+  if (workspace_bytes < mmr_search_workspace_bytes(ix, B, k)) return fail(MMR_ERR_WORKSPACE, "workspace too small");
+  std::vector<std::vector<std::pair<uint32_t, uint32_t>>> per_query(B);
+  bool single_shared = true;
+  for (int b = 0; b < B; ++b) {
+    if (range_off_host[b + 1] < range_off_host[b]) return fail(MMR_ERR_INVALID, "range offsets must be ascending");
+    for (int32_t r = range_off_host[b]; r < range_off_host[b + 1]; ++r) {
+      const int64_t lo = ranges_host[2 * r], hi = ranges_host[2 * r + 1];
+      if (lo < 0 || hi < lo || hi > ix->n_rows) return fail(MMR_ERR_INVALID, "query %d: bad row range [%lld, %lld)", b, (long long)lo, (long long)hi);
+      if (hi > lo) per_query[b].push_back({uint32_t(lo), uint32_t(hi)});
+    }
+    if (per_query[b].size() != 1 || per_query[b] != per_query[0]) single_shared = false;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
+  if (single_shared) {  // everyone scans the same single range: the uniform kernels apply
+    const uint32_t r0 = per_query[0][0].first, r1 = per_query[0][0].second;
+#ifdef MMR_WITH_UMMA
+    if (umma_preferred(ix->dtype, ix->dim, B, k, int64_t(r1) - r0)) {
+      int rc = umma_search(ix->umma, ix->rows, ix->n_rows, ix->dim, ix->dtype, ix->sm_count, queries_dev, B, k, r0, r1,
+                           ix->row_base, out_scores_dev, out_rows_dev,
+                           ws + mmr_search_workspace_bytes(ix, B, k) - umma_workspace_bytes(ix->sm_count, ix->dim, B, k),
+                           st, g_err);
+      if (rc == MMR_OK) {
+        g_launches += umma_launches_per_search();
+        g_last_kernel = 2;
+      }
+      return rc;
+    }
+#endif
+    return search_uniform_stream(ix, queries_dev, B, k, r0, r1, out_scores_dev, out_rows_dev, ws, st);
+  }
+  return search_varlen_stream(ix, queries_dev, per_query, k, out_scores_dev, out_rows_dev, ws, workspace_bytes, st);
 }
 
 static int ensure_staging(mmr_index* ix, int B, int k) {

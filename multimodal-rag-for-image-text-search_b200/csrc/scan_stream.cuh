@@ -275,7 +275,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) scan_stream_kernel(const Stream
       const int r = vi / NQ;
       const int myq = vi % NQ;
       const uint32_t row = row_begin + uint32_t(c) * C::R + uint32_t(r);
-      const bool owner = (lane % LPV == 0) && row < row_end;
+      // NaN scores (tombstoned rows are overwritten with NaN by the store) never enter a list
+      const bool owner = (lane % LPV == 0) && row < row_end && score == score;
       const uint64_t key = make_key(score, row);
 #pragma unroll
       for (int qi = 0; qi < NQ; ++qi) {

@@ -81,6 +81,39 @@ class ResidentIndex:
                                                  int(normalize), _stream_ptr(device)))
         return cls(dst, seg_offsets, row_base)
 
+    def update(self, rows: torch.Tensor, n_rows: Optional[int] = None, seg_offsets=None) -> None:
+        """Re-point the handle at grown / rewritten rows (same dim and dtype) after an upsert; the first n_rows rows
+        of `rows` are live (`rows` may be a larger capacity buffer)."""
+        if rows.dtype != self.rows.dtype or rows.shape[1] != self.dim or not rows.is_contiguous():
+            raise ValueError("update needs a contiguous tensor of the same dtype and dim")
+        n = int(rows.shape[0]) if n_rows is None else int(n_rows)
+        self.seg_offsets = None if seg_offsets is None else np.ascontiguousarray(seg_offsets, dtype=np.int64)
+        nseg = 0 if self.seg_offsets is None else len(self.seg_offsets) - 1
+        segp = None if self.seg_offsets is None else self.seg_offsets.ctypes.data
+        N.check(N.lib().mmr_index_update(self._handle, n, rows.data_ptr() if n else None, segp, nseg))
+        self.rows, self.n_rows = rows, n
+
+    def search_ranges(self, queries: torch.Tensor, k: int, ranges) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Like `search`, but query b scans the explicit row ranges `ranges[b]` = [(lo, hi), ...]."""
+        if queries.dim() == 1:
+            queries = queries[None, :]
+        b = int(queries.shape[0])
+        k = max(int(k), 1)
+        off = np.zeros(b + 1, dtype=np.int32)
+        flat = []
+        for i, rq in enumerate(ranges):
+            flat.extend(rq)
+            off[i + 1] = len(flat)
+        arr = np.ascontiguousarray(flat, dtype=np.int64).reshape(-1, 2) if flat else np.zeros((1, 2), np.int64)
+        scores = torch.empty((b, k), dtype=torch.float32, device=self.device)
+        rows = torch.empty((b, k), dtype=torch.int64, device=self.device)
+        ws = self._workspace(b, k)
+        with torch.cuda.device(self.device):
+            N.check(N.lib().mmr_search_ranges(self._handle, queries.data_ptr(), b, k, off.ctypes.data, arr.ctypes.data,
+                                              scores.data_ptr(), rows.data_ptr(), ws.data_ptr(), ws.numel(),
+                                              _stream_ptr(self.device)))
+        return scores, rows
+
     def close(self) -> None:
         if self._handle:
             N.lib().mmr_index_destroy(self._handle)

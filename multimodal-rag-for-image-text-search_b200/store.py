@@ -51,7 +51,18 @@ def _unit_f32(vector: Sequence[float]) -> np.ndarray:
 
 
 class _Collection:
-    """Host master copy (columns in insertion order) + the tenant-sorted resident copy on the GPU."""
+    """Host master copy (columns in insertion order) + the resident copy on the GPU.
+
+    Resident layout = [base: tenant-sorted rows of the last compaction][delta segments appended since].  An upsert
+    tombstones the replaced rows (their resident vectors are overwritten with NaN, which the kernels never
+    return) and appends the new rows grouped by tenant, so a tenant owns a short list of row ranges and every
+    search scans exactly those (mmr_search_ranges).  A compaction (full tenant-sorted rebuild) runs when the
+    buffer is full, tombstones exceed a quarter of it, or a tenant has collected more than MAX_RANGES ranges.
+    This is the incremental refresh path of SURVEY 8f: an upsert no longer re-uploads the table.
+    """
+
+    MAX_RANGES = 8
+    MAX_TOMB_FRACTION = 0.25
 
     def __init__(self, name: str, device: torch.device, dtype: str) -> None:
         self.name = name
@@ -63,38 +74,53 @@ class _Collection:
         self.modality: List[str] = []
         self.meta: List[Optional[str]] = []
         self._blocks: List[np.ndarray] = []     # f32 [n_i, D] blocks, concatenation = host row order
+        self._block_start: List[int] = []
         self._alive: List[bool] = []
         self._where: Dict[str, int] = {}        # chunk_id -> host row (alive rows only)
-        self._dirty = True
+        # resident state
         self._resident: Optional[ResidentIndex] = None
-        self._perm = np.empty(0, np.int64)      # resident row -> host row
-        self._seg_of: Dict[str, int] = {}
+        self._buf: Optional[torch.Tensor] = None   # capacity buffer [cap, D]
+        self._n_res = 0
+        self._perm = np.empty(0, np.int64)         # resident row -> host row
+        self._res_of: Dict[int, int] = {}          # host row -> resident row
+        self._ranges: Dict[str, List[List[int]]] = {}
+        self._tomb = 0
+        self._pending_rows: List[int] = []         # host rows not yet resident
+        self._pending_tomb: List[int] = []         # resident rows to overwrite with NaN
+        self._force_rebuild = True
         self.rebuilds = 0
+        self.appends = 0
 
     # -- writes -------------------------------------------------------------------------------
     def __len__(self) -> int:
         return len(self._where)
 
+    def _kill(self, host_row: int) -> None:
+        self._alive[host_row] = False           # table.delete("chunk_id == '...'") (lancedb_store.py:91-92)
+        res = self._res_of.pop(host_row, None)
+        if res is not None:
+            self._pending_tomb.append(res)
+
     def _append(self, chunk_ids, user_ids, doc_ids, modalities, metas, emb: np.ndarray) -> None:
         base = len(self.chunk_id)
-        for j, cid in enumerate(chunk_ids):
-            old = self._where.get(cid)
-            if old is not None:
-                self._alive[old] = False          # table.delete("chunk_id == '...'") (:91-92)
-            self._where[cid] = base + j
+        emb = np.ascontiguousarray(emb, dtype=np.float32)
+        if self._blocks and emb.shape[1] != self._blocks[0].shape[1]:
+            raise ValueError(f"{self.name}: embedding length {emb.shape[1]} != {self._blocks[0].shape[1]} already stored")
         self.chunk_id.extend(chunk_ids)
         self.user_id.extend(user_ids)
         self.document_id.extend(doc_ids)
         self.modality.extend(modalities)
         self.meta.extend(metas)
         self._alive.extend([True] * len(chunk_ids))
-        # duplicates inside one batch: only the last one stays alive (delete-all-then-add would keep both in
-        # LanceDB; a chunk id is a primary key everywhere else in the reference, so we keep it unique)
         for j, cid in enumerate(chunk_ids):
-            if self._where[cid] != base + j:
-                self._alive[base + j] = False
-        self._blocks.append(np.ascontiguousarray(emb, dtype=np.float32))
-        self._dirty = True
+            old = self._where.get(cid)
+            if old is not None:
+                # an id is a primary key everywhere else in the reference: the newest row wins (also inside a batch)
+                self._kill(old)
+            self._where[cid] = base + j
+        self._block_start.append(base)
+        self._blocks.append(emb)
+        self._pending_rows.extend(base + j for j in range(len(chunk_ids)) if self._alive[base + j])
 
     def upsert(self, rows: Iterable[VectorRow]) -> List[str]:
         rows = list(rows)
@@ -112,35 +138,96 @@ class _Collection:
         """Bulk load of rows that are already normalised (what a LanceDB table holds)."""
         self._append(list(chunk_ids), [str(u) for u in user_ids], list(doc_ids), list(modalities), list(metas), emb)
 
+    def _host_rows(self, idx: np.ndarray) -> np.ndarray:
+        """f32 embeddings of the given host rows."""
+        if len(self._blocks) > 1:
+            self._blocks = [np.concatenate(self._blocks, axis=0)]
+            self._block_start = [0]
+        return self._blocks[0][idx]
+
     # -- resident copy ------------------------------------------------------------------------
     def _rebuild(self) -> None:
+        """Compaction: tenant-sorted base, no deltas, no tombstones."""
         alive = np.nonzero(np.asarray(self._alive, dtype=bool))[0]
+        self._pending_rows, self._pending_tomb, self._tomb = [], [], 0
+        self._force_rebuild = False
+        if self._resident is not None:
+            self._resident.close()
+            self._resident = None
         if alive.size == 0:
-            self._resident, self._perm, self._seg_of = None, np.empty(0, np.int64), {}
-            self._dirty = False
+            self._buf, self._n_res, self._perm, self._res_of, self._ranges = None, 0, np.empty(0, np.int64), {}, {}
             return
-        dims = {b.shape[1] for b in self._blocks}
-        if len(dims) != 1:
-            raise ValueError(f"{self.name}: rows of different embedding lengths {sorted(dims)} (the scan needs one dim)")
-        mat = self._blocks[0] if len(self._blocks) == 1 else np.concatenate(self._blocks, axis=0)
-        self._blocks = [mat]
-        users = np.asarray(self.user_id, dtype=object)[alive]
-        uniq, inv = np.unique(users.astype(str), return_inverse=True)
+        users = np.asarray(self.user_id, dtype=object)[alive].astype(str)
+        uniq, inv = np.unique(users, return_inverse=True)
         order = np.argsort(inv, kind="stable")            # tenant-sorted, host order kept inside a tenant
         self._perm = alive[order]
         counts = np.bincount(inv, minlength=len(uniq))
         seg = np.zeros(len(uniq) + 1, dtype=np.int64)
         np.cumsum(counts, out=seg[1:])
-        self._seg_of = {str(u): i for i, u in enumerate(uniq)}
-        if self._resident is not None:
-            self._resident.close()
-        self._resident = ResidentIndex.from_f32(mat[self._perm], seg, dtype=self.dtype, device=self.device)
-        self._dirty = False
+        n = int(alive.size)
+        cap = max(n + 4096, int(n * 1.25))
+        base = ResidentIndex.from_f32(self._host_rows(self._perm), None, dtype=self.dtype, device=self.device)
+        self._buf = torch.empty((cap, base.dim), dtype=base.rows.dtype, device=self.device)
+        self._buf[:n].copy_(base.rows)
+        base.close()
+        self._n_res = n
+        self._resident = ResidentIndex(self._buf[:n])
+        self._resident.update(self._buf, n)
+        self._res_of = {int(h): i for i, h in enumerate(self._perm)}
+        self._ranges = {str(u): [[int(seg[i]), int(seg[i + 1])]] for i, u in enumerate(uniq)}
         self.rebuilds += 1
 
+    def _apply_deltas(self) -> None:
+        """Tombstone replaced rows and append the pending rows as per-tenant delta segments."""
+        if self._pending_tomb:
+            idx = torch.as_tensor(self._pending_tomb, dtype=torch.int64, device=self.device)
+            self._buf.index_fill_(0, idx, float("nan"))
+            self._tomb += len(self._pending_tomb)
+            self._pending_tomb = []
+        rows = [h for h in self._pending_rows if self._alive[h]]
+        self._pending_rows = []
+        if rows:
+            rows = np.asarray(rows, dtype=np.int64)
+            users = np.asarray([self.user_id[h] for h in rows], dtype=object).astype(str)
+            order = np.argsort(users, kind="stable")       # group the batch by tenant, arrival order inside
+            rows, users = rows[order], users[order]
+            m = len(rows)
+            lo = self._n_res
+            delta = ResidentIndex.from_f32(self._host_rows(rows), None, dtype=self.dtype, device=self.device)
+            self._buf[lo:lo + m].copy_(delta.rows)
+            delta.close()
+            self._perm = np.concatenate([self._perm, rows])
+            for j, h in enumerate(rows):
+                self._res_of[int(h)] = lo + j
+            start = 0
+            while start < m:
+                end = start
+                while end < m and users[end] == users[start]:
+                    end += 1
+                rl = self._ranges.setdefault(str(users[start]), [])
+                if rl and rl[-1][1] == lo + start:
+                    rl[-1][1] = lo + end                      # contiguous with the tenant's last range
+                else:
+                    rl.append([lo + start, lo + end])
+                start = end
+            self._n_res = lo + m
+            self.appends += 1
+        self._resident.update(self._buf, self._n_res)
+
     def resident(self) -> Optional[ResidentIndex]:
-        if self._dirty:
+        if not self._force_rebuild and not self._pending_rows and not self._pending_tomb:
+            return self._resident
+        n_new = sum(1 for h in self._pending_rows if self._alive[h])
+        need_rebuild = (
+            self._force_rebuild or self._resident is None or self._buf is None
+            or self._n_res + n_new > self._buf.shape[0]
+            or (self._tomb + len(self._pending_tomb)) > self.MAX_TOMB_FRACTION * max(self._n_res, 1)
+            or any(len(r) >= self.MAX_RANGES for r in self._ranges.values())
+        )
+        if need_rebuild:
             self._rebuild()
+        else:
+            self._apply_deltas()
         return self._resident
 
     # -- reads --------------------------------------------------------------------------------
@@ -152,12 +239,19 @@ class _Collection:
         out: List[List[Dict[str, Any]]] = [[] for _ in user_ids]
         if res is None:
             return out
-        segs = [self._seg_of.get(str(u), -1) for u in user_ids]
-        live = [i for i, s in enumerate(segs) if s >= 0]
+        ranges = [self._ranges.get(str(u)) for u in user_ids]
+        live = [i for i, r in enumerate(ranges) if r]
         if not live:
             return out
         q = np.ascontiguousarray(vectors[live], dtype=np.float32)
-        scores, rows = res.search_host(q, limit, [segs[i] for i in live])
+        if all(len(ranges[i]) == 1 and ranges[i] == ranges[live[0]] for i in live):
+            # one shared range: host-buffer C call (H2D + scan + D2H inside the library)
+            lo, hi = ranges[live[0]][0]
+            res.update(self._buf, self._n_res, seg_offsets=[lo, hi])
+            scores, rows = res.search_host(q, limit, [0] * len(live))
+        else:
+            s_dev, r_dev = res.search_ranges(torch.from_numpy(q).to(self.device), limit, [ranges[i] for i in live])
+            scores, rows = s_dev.cpu().numpy(), r_dev.cpu().numpy()
         one = np.float32(1.0)
         for j, i in enumerate(live):
             hits = []

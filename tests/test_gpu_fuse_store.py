@@ -167,3 +167,69 @@ def test_arrow_load_and_retrieve_end_to_end(mmr):
     assert out["combined"][0].cpu().tolist() == [f["combined_score"] for f in fused]
     assert bool(out["low_conf"][0]) is retrieve._confidence_low(fused)
     cache.clear_all_caches()
+
+
+def test_incremental_upserts_track_the_oracle_store(mmr):
+    """SURVEY 8f rank 1 -- index refresh without re-uploading the table: upserts append per-tenant delta segments and
+    tombstone replaced rows (NaN rows are never returned); results keep matching the oracle store after every step and
+    compactions stay rare."""
+    rng = np.random.default_rng(5)
+    users = ["a", "b", "c", "d"]
+    gpu, cpu = mmr.B200Store(), ofs.OracleStore()
+
+    def make(ids, user_of):
+        return [SimpleNamespace(chunk_id=f"t{i}", user_id=user_of(i), document_id="d", modality="text",
+                                embedding=rng.standard_normal(384).astype(np.float32).tolist(), meta={"i": int(i)}) for i in ids]
+
+    def check(tag):
+        for u in users + ["nobody"]:
+            q = rng.standard_normal(384).astype(np.float32)
+            got, want = gpu.search_text(u, q.tolist(), 10), cpu.search_text(u, q.tolist(), 10)
+            assert len(got) == len(want), (tag, u)
+            if want:
+                kth = want[-1]["score"]
+                ws = {w["chunk_id"]: w["score"] for w in want}
+                for g in got:
+                    assert (g["chunk_id"] in ws and abs(g["score"] - ws[g["chunk_id"]]) <= util.TOL_BF16) or \
+                        g["score"] >= kth - 2 * util.TOL_BF16, (tag, u, g)
+                assert {w["chunk_id"] for w in want if w["score"] > kth + 2 * util.TOL_BF16} <= {g["chunk_id"] for g in got}
+        qs = rng.standard_normal((6, 384)).astype(np.float32)
+        us = ["a", "c", "b", "a", "nobody", "d"]
+        batch = gpu.search_text_batch(us, qs, 5)             # mixed tenants, several ranges each -> one ranges launch
+        for u, q, b in zip(us, qs, batch):
+            assert [h["chunk_id"] for h in b] == [h["chunk_id"] for h in gpu.search_text(u, q.tolist(), 5)]
+
+    first = make(range(6000), lambda i: users[i % 4])
+    for st in (gpu, cpu):
+        st.upsert_text_vectors([mmr.VectorRow(**r.__dict__) for r in first] if st is gpu else first)
+    check("initial")
+    assert gpu._text_table.rebuilds == 1
+    next_id = 6000
+    for step in range(6):
+        new = make(range(next_id, next_id + 40), lambda i: users[(i * 7) % 4])
+        next_id += 40
+        over = make(rng.choice(next_id - 40, size=25, replace=False), lambda i: users[i % 4])   # replace existing chunks
+        batch = new + over
+        old_vec = None
+        if step == 2:
+            victim = over[0]
+            hr = gpu._text_table._where[victim.chunk_id]
+            old_vec = gpu._text_table._host_rows(np.array([hr]))[0].copy()
+        for st in (gpu, cpu):
+            st.upsert_text_vectors([mmr.VectorRow(**r.__dict__) for r in batch] if st is gpu else batch)
+        check(f"step{step}")
+        if old_vec is not None:
+            hits = gpu.search_text(victim.user_id, old_vec.tolist(), 3)    # the replaced vector is gone (tombstone)
+            assert all(not (h["chunk_id"] == victim.chunk_id and h["score"] > 0.99) for h in hits)
+    coll = gpu._text_table
+    assert coll.rebuilds == 1 and coll.appends == 6, (coll.rebuilds, coll.appends)
+    assert coll._tomb == 6 * 25 and max(len(r) for r in coll._ranges.values()) <= 7
+    # enough deltas force a compaction; answers stay the same
+    for step in range(3):
+        batch = make(range(next_id, next_id + 8), lambda i: users[i % 4])
+        next_id += 8
+        for st in (gpu, cpu):
+            st.upsert_text_vectors([mmr.VectorRow(**r.__dict__) for r in batch] if st is gpu else batch)
+        check(f"compaction{step}")
+    assert coll.rebuilds >= 2 and coll._tomb == 0
+    assert gpu.get_index_version("a") >= 10
