@@ -161,8 +161,8 @@ def test_arrow_load_and_retrieve_end_to_end(mmr):
     assert retrieve.retrieve("u1", "what is in the picture?") is fused              # cache hit, same version
     assert retrieve.retrieve("nobody", "x") == []
     # device fusion of the same request agrees with the host fusion bit for bit
-    ts, tr = store._text_table.resident().search(torch.from_numpy(qt[None]).cuda(), 50, [store._text_table._seg_of["u1"]])
-    is_, ir = store._image_table.resident().search(torch.from_numpy(qi[None]).cuda(), 12, [store._image_table._seg_of["u1"]])
+    ts, tr = store._text_table.resident().search_ranges(torch.from_numpy(qt[None]).cuda(), 50, [store._text_table._ranges["u1"]])
+    is_, ir = store._image_table.resident().search_ranges(torch.from_numpy(qi[None]).cuda(), 12, [store._image_table._ranges["u1"]])
     out = mmr.fuse((ts, tr), (is_, ir), 4, 0.25)
     assert out["combined"][0].cpu().tolist() == [f["combined_score"] for f in fused]
     assert bool(out["low_conf"][0]) is retrieve._confidence_low(fused)
