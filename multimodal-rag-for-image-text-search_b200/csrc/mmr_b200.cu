@@ -14,7 +14,7 @@
 #include "common.cuh"
 #include "scan_stream.cuh"
 #ifdef MMR_WITH_UMMA
-#include "scan_umma.cuh"
+#include "scan_umma2.cuh"
 #endif
 
 using namespace mmr;
@@ -62,6 +62,7 @@ struct mmr_index {
   int cap_b = 0, cap_k = 0;
 #ifdef MMR_WITH_UMMA
   mutable UmmaIndexState umma;
+  mutable Umma2IndexState umma2;
 #endif
 };
 
@@ -134,6 +135,7 @@ extern "C" int mmr_index_update(mmr_index* ix, int64_t n_rows, const void* rows_
   ix->rows = rows_dev;
 #ifdef MMR_WITH_UMMA
   ix->umma.valid = false;
+  ix->umma2.valid = false;
 #endif
   return set_segments(ix, seg, nseg);
 }
@@ -444,7 +446,7 @@ extern "C" int mmr_search(const mmr_index* ix, const float* queries_dev, const i
   if (uniform) {
 #ifdef MMR_WITH_UMMA
     if (umma_preferred(ix->dtype, ix->dim, B, k, int64_t(ranges[0].second) - ranges[0].first)) {
-      int rc = umma_search(ix->umma, ix->rows, ix->n_rows, ix->dim, ix->dtype, ix->sm_count, queries_dev, B, k, ranges[0].first,
+      int rc = umma_search(ix->umma, ix->umma2, ix->rows, ix->n_rows, ix->dim, ix->dtype, ix->sm_count, queries_dev, B, k, ranges[0].first,
                            ranges[0].second, ix->row_base, out_scores_dev, out_rows_dev,
                            ws + mmr_search_workspace_bytes(ix, B, k) - umma_workspace_bytes(ix->sm_count, ix->dim, B, k),
                            st, g_err);
@@ -491,7 +493,7 @@ extern "C" int mmr_search_ranges(const mmr_index* ix, const float* queries_dev, 
     const uint32_t r0 = per_query[0][0].first, r1 = per_query[0][0].second;
 #ifdef MMR_WITH_UMMA
     if (umma_preferred(ix->dtype, ix->dim, B, k, int64_t(r1) - r0)) {
-      int rc = umma_search(ix->umma, ix->rows, ix->n_rows, ix->dim, ix->dtype, ix->sm_count, queries_dev, B, k, r0, r1,
+      int rc = umma_search(ix->umma, ix->umma2, ix->rows, ix->n_rows, ix->dim, ix->dtype, ix->sm_count, queries_dev, B, k, r0, r1,
                            ix->row_base, out_scores_dev, out_rows_dev,
                            ws + mmr_search_workspace_bytes(ix, B, k) - umma_workspace_bytes(ix->sm_count, ix->dim, B, k),
                            st, g_err);
@@ -645,7 +647,7 @@ extern "C" int mmr_debug_umma_scores(const mmr_index* ix, const float* queries_d
   if (B <= 0 || row_begin < 0 || row_end > ix->n_rows || row_end <= row_begin || out_ld < row_end - row_begin)
     return fail(MMR_ERR_INVALID, "bad range");
   if (workspace_bytes < umma_workspace_bytes(ix->sm_count, ix->dim, B, 10)) return fail(MMR_ERR_WORKSPACE, "workspace too small");
-  int rc = umma_search(ix->umma, ix->rows, ix->n_rows, ix->dim, ix->dtype, ix->sm_count, queries_dev, B, 10, uint32_t(row_begin),
+  int rc = umma_search(ix->umma, ix->umma2, ix->rows, ix->n_rows, ix->dim, ix->dtype, ix->sm_count, queries_dev, B, 10, uint32_t(row_begin),
                        uint32_t(row_end), 0, nullptr, nullptr, static_cast<uint8_t*>(workspace_dev),
                        static_cast<cudaStream_t>(stream), g_err, out_scores_dev, out_ld);
   if (rc == MMR_OK) g_launches += 2;

@@ -581,115 +581,3 @@ inline bool umma_preferred(int dtype, int dim, int B, int k, int64_t nrows) {
   return umma_plan_stages(dim, k, nullptr) >= 2;
 }
 }  // namespace mmr
-
-namespace mmr {
-#ifdef __CUDACC__
-// One K2 search: prep queries -> scan (grid = qtiles x row slots) -> per-query merge.  `ws` is the K2 slice of the
-// workspace (umma_workspace_bytes).  dump != nullptr runs the raw-score debug variant instead of top-k.
-inline int umma_search(UmmaIndexState& st, const void* rows, int64_t n_rows, int dim, int dtype, int sm_count,
-                       const float* queries, int B, int k, uint32_t r0, uint32_t r1, int64_t row_base, float* out_s,
-                       int64_t* out_r, uint8_t* ws, cudaStream_t stream, std::string& err, float* dump = nullptr,
-                       int64_t dump_ld = 0) {
-  if (!st.valid || st.rows != rows || st.n_rows != n_rows) {
-    if (!umma_make_map(&st.map, rows, n_rows, dim, dtype == MMR_BF16)) {
-      err = "cuTensorMapEncodeTiled failed for the index";
-      return MMR_ERR_CUDA;
-    }
-    st.valid = true;
-    st.rows = rows;
-    st.n_rows = n_rows;
-  }
-  // Operand placement, chosen from measurements on B200 (profiles/r01_k2_sweep.md): one query tile (B <= 128) is
-  // HBM-bound and fastest with both operands in shared memory and 4 accumulators; several query tiles are
-  // tensor-bound and fastest with the query tile in tensor memory (half the shared-memory reads per MMA, 13-deep
-  // ring).  MMR_UMMA_MODE=ss|ts overrides.
-  const char* mode = getenv("MMR_UMMA_MODE");
-  bool ts = umma_qtiles(B) > 1;
-  if (mode && mode[0] == 's') ts = false;
-  if (mode && mode[0] == 't') ts = true;
-  if (dim / 2 + 2 * K2_NT > 512) ts = false;
-  size_t smem_bytes = 0;
-  const int stages = umma_plan_stages(dim, k, &smem_bytes, ts);
-  if (stages < 2) {
-    err = "K2: shared memory plan does not fit";
-    return MMR_ERR_UNSUPPORTED;
-  }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(scan_umma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_LIMIT);
-    cudaFuncSetAttribute(scan_umma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_LIMIT);
-    cudaFuncSetAttribute(scan_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_LIMIT);
-    cudaFuncSetAttribute(scan_umma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_LIMIT);
-    attr_set = true;
-  }
-  __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(ws);
-  uint64_t* partial = reinterpret_cast<uint64_t*>(ws + umma_align(size_t(B) * dim * 2));
-  const int ctas_max = std::max(sm_count, std::min(umma_qtiles(B), sm_count));
-  float* probe = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(partial) + umma_align(size_t(ctas_max) * K2_BM * k * 8));
-  float* floor = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(probe) + umma_align(size_t(ctas_max) * K2_BM * 4));
-  const char* noprobe = getenv("MMR_UMMA_NOPROBE");
-  if (dtype == MMR_BF16) prep_queries_kernel<__nv_bfloat16><<<(B + 3) / 4, 128, 0, stream>>>(queries, qb, B, dim);
-  else prep_queries_kernel<__half><<<(B + 3) / 4, 128, 0, stream>>>(queries, reinterpret_cast<__half*>(qb), B, dim);
-  const int max_q_per_pass = sm_count * K2_BM;
-  for (int q0 = 0; q0 < B; q0 += max_q_per_pass) {
-    const int bq = std::min(B - q0, max_q_per_pass);
-    CUtensorMap tm_q;
-    if (!umma_make_map(&tm_q, qb + size_t(q0) * dim, bq, dim, dtype == MMR_BF16)) {
-      err = "cuTensorMapEncodeTiled failed for the queries";
-      return MMR_ERR_CUDA;
-    }
-    UmmaParams p{};
-    p.ks = dim / 64;
-    p.idesc = umma_idesc_m128_n128(dtype == MMR_BF16);
-    p.nstages = stages;
-    p.k = k;
-    p.B = bq;
-    p.row_begin = r0;
-    p.row_end = r1;
-    p.n_qtiles = umma_qtiles(bq);
-    const int64_t ntiles = (int64_t(r1) - r0 + K2_NT - 1) / K2_NT;
-    p.n_rslots = int(std::max<int64_t>(1, std::min<int64_t>(sm_count / p.n_qtiles, ntiles)));
-    p.partial = partial;
-    p.qbf16 = qb + size_t(q0) * dim;
-    p.dump = dump ? dump + int64_t(q0) * dump_ld : nullptr;
-    p.dump_ld = dump_ld;
-    const int grid = p.n_qtiles * p.n_rslots;
-    // probe pass: worth it when every CTA streams many tiles (the warm-up it removes is ~k ln(n/k) inserts/thread)
-    const int64_t tiles_per_cta = ntiles / p.n_rslots;
-    if (!dump && !(noprobe && noprobe[0] == '1') && tiles_per_cta >= 8 && p.n_rslots >= k) {
-      UmmaParams pp = p;
-      pp.probe_out = probe;
-      pp.probe_tiles = int(std::max<int64_t>(1, std::min<int64_t>(16, tiles_per_cta / 24)));
-      if (ts) scan_umma_kernel<false, true><<<grid, K2_THREADS, smem_bytes, stream>>>(tm_q, st.map, pp);
-      else scan_umma_kernel<false, false><<<grid, K2_THREADS, smem_bytes, stream>>>(tm_q, st.map, pp);
-      const int wpb = 4;
-      if (k <= 32) probe_floor_kernel<1><<<(bq + wpb - 1) / wpb, wpb * 32, 0, stream>>>(probe, p.n_qtiles, p.n_rslots, bq, k, floor + q0);
-      else probe_floor_kernel<2><<<(bq + wpb - 1) / wpb, wpb * 32, 0, stream>>>(probe, p.n_qtiles, p.n_rslots, bq, k, floor + q0);
-      p.floor = floor + q0;
-    }
-    if (dump) {
-      if (ts) scan_umma_kernel<true, true><<<grid, K2_THREADS, smem_bytes, stream>>>(tm_q, st.map, p);
-      else scan_umma_kernel<true, false><<<grid, K2_THREADS, smem_bytes, stream>>>(tm_q, st.map, p);
-    } else {
-      if (ts) scan_umma_kernel<false, true><<<grid, K2_THREADS, smem_bytes, stream>>>(tm_q, st.map, p);
-      else scan_umma_kernel<false, false><<<grid, K2_THREADS, smem_bytes, stream>>>(tm_q, st.map, p);
-      const int wpb = 4;
-      if (k <= 32)
-        merge_partials_kernel<1><<<(bq + wpb - 1) / wpb, wpb * 32, 0, stream>>>(partial, p.n_qtiles, p.n_rslots, bq, k,
-                                                                              out_s + size_t(q0) * k,
-                                                                              out_r + size_t(q0) * k, row_base);
-      else
-        merge_partials_kernel<2><<<(bq + wpb - 1) / wpb, wpb * 32, 0, stream>>>(partial, p.n_qtiles, p.n_rslots, bq, k,
-                                                                              out_s + size_t(q0) * k,
-                                                                              out_r + size_t(q0) * k, row_base);
-    }
-  }
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) {
-    err = std::string("K2 launch failed: ") + cudaGetErrorString(e);
-    return MMR_ERR_CUDA;
-  }
-  return MMR_OK;
-}
-#endif
-}  // namespace mmr

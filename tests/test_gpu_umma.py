@@ -23,10 +23,12 @@ def _bf16(x):
     return torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy()
 
 
-@pytest.fixture(params=["ts", "ss"])
+@pytest.fixture(params=["ts", "ss", "pair"])
 def umma_mode(request, monkeypatch):
-    """ts = query tile as the A operand in tensor memory (default); ss = both operands in shared memory."""
-    monkeypatch.setenv("MMR_UMMA_MODE", request.param)
+    """ts = query tile as the A operand in tensor memory; ss = both operands in shared memory;
+    pair = ts on CTA pairs (tcgen05.mma.cta_group::2, M = 256) for batches of at least two query tiles."""
+    monkeypatch.setenv("MMR_UMMA_MODE", "ts" if request.param == "pair" else request.param)
+    monkeypatch.setenv("MMR_UMMA_PAIR", "1" if request.param == "pair" else "0")
     return request.param
 
 
