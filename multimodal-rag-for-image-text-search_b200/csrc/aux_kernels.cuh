@@ -142,6 +142,8 @@ __global__ void merge_wait_kernel(const uint8_t* __restrict__ xbuf, int parity, 
                                   int64_t* __restrict__ out_rows, uint64_t timeout_ns) {
   const int lane = threadIdx.x & 31;
   const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // let the next search's scan start while we wait for the peers (it uses the other slot parity)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (qi >= B) return;
   const uint32_t* flags = reinterpret_cast<const uint32_t*>(xbuf) + parity * MMR_XCHG_MAX_PEERS;
   bool ok = true;

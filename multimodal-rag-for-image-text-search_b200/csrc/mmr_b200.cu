@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -247,9 +248,22 @@ static int launch_stream_t(const StreamParams& p, int grid, cudaStream_t st) {
                                   C::SMEM_BYTES));
     attr_set[dev] = true;
   }
-  scan_stream_kernel<E, D, NQ, KPL><<<grid, K1_THREADS, C::SMEM_BYTES, st>>>(p);
+  // MMR_PDL=1 (opt-in): launch with programmatic stream serialization so consecutive searches on one stream overlap
+  // tail and head.  Contract: the queries of a search must not be produced by the kernel launched immediately before
+  // it on the same stream (the scan starts before that kernel's memory is guaranteed visible).
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(K1_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  const char* pdl = getenv("MMR_PDL");
+  attr[0].val.programmaticStreamSerializationAllowed = (p.items == nullptr && pdl && pdl[0] == '1') ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, scan_stream_kernel<E, D, NQ, KPL>, p));
   g_launches++;
-  CUDA_TRY(cudaGetLastError());
   return MMR_OK;
 }
 

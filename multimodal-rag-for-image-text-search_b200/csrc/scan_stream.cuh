@@ -149,6 +149,11 @@ __global__ void __launch_bounds__(K1_THREADS, 1) scan_stream_kernel(const Stream
   const int warp = threadIdx.x >> 5;
   const int k = p.k;
 
+  // Programmatic dependent launch: the next search on this stream may start its CTAs as ours retire (its scan only
+  // reads the index and its own queries); it waits (griddepcontrol.wait below) before it touches the shared workspace.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (p.items != nullptr) asm volatile("griddepcontrol.wait;" ::: "memory");  // varlen writes partials as it goes
+
   // ---- this warp's ring ----
   const uint32_t ring0 = smem_u32(smem) + uint32_t(warp) * (C::S * C::STAGE_BYTES);
   const uint32_t bar0 = smem_u32(bars) + uint32_t(warp) * (C::S * 8);
@@ -293,6 +298,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) scan_stream_kernel(const Stream
     // ------------------------------ uniform mode ------------------------------
     scan_range(p.row_begin, p.row_end, gwarp, twarps);
 
+    // the previous search on this stream must be completely done before we touch partials / ticket / outputs
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // warp lists -> shared memory (ring is idle now: every issued copy has been consumed)
     __syncthreads();
     uint64_t* wk = reinterpret_cast<uint64_t*>(smem);  // [NW][NQ][KSLOTS]
@@ -326,8 +333,18 @@ __global__ void __launch_bounds__(K1_THREADS, 1) scan_stream_kernel(const Stream
       WarpTopK<KPL> m;
       m.clear();
       uint64_t t = 0ull;
-      for (int part = warp; part < nparts; part += K1_NW)
-        t = m.template merge_from<true>(p.partial + (size_t(part) * NQ + qi) * k, k, 1, t, k, lane);
+      {
+        // this warp's share of the per-CTA lists: parts warp, warp + NW, ...; candidates are visited position-major
+        // (all heads first) so the threshold rises early, and fetched 8 per lane per round trip through L2
+        const int nmine = (nparts - warp + K1_NW - 1) / K1_NW;
+        const uint64_t* base = p.partial;
+        t = m.template merge_batched<8>(
+            [&](int i) -> uint64_t {
+              const int pos = i / nmine, part = warp + (i % nmine) * K1_NW;
+              return __ldcg(reinterpret_cast<const unsigned long long*>(base) + (size_t(part) * NQ + qi) * k + pos);
+            },
+            nmine * k, t, k, lane);
+      }
       __syncthreads();
 #pragma unroll
       for (int j = 0; j < KPL; ++j) wk[warp * C::KSLOTS + j * 32 + lane] = m.key[j];

@@ -446,18 +446,13 @@ __global__ void merge_partials_kernel(const uint64_t* __restrict__ partial, int 
   WarpTopK<KPL> m;
   m.clear();
   uint64_t thr = 0ull;
-  const int total = n_rslots * k;
-  for (int i0 = 0; i0 < total; i0 += 32) {
-    const int i = i0 + lane;
-    const bool valid = i < total;
-    uint64_t c = 0ull;
-    if (valid) {
-      // round-robin over the lists first: the heads (best keys) arrive early and raise the threshold fast
-      const int rs = i % n_rslots, j = i / n_rslots;
-      c = partial[(size_t(qt * n_rslots + rs) * K2_BM + ql) * k + j];
-    }
-    thr = m.offer(c, valid && c != 0ull, thr, k, lane);
-  }
+  // round-robin over the lists (entry j of every list before entry j+1), 8 loads in flight per lane
+  thr = m.template merge_batched<8>(
+      [&](int i) -> uint64_t {
+        const int rs = i % n_rslots, j = i / n_rslots;
+        return partial[(size_t(qt * n_rslots + rs) * K2_BM + ql) * k + j];
+      },
+      n_rslots * k, thr, k, lane);
 #pragma unroll
   for (int j = 0; j < KPL; ++j) {
     const int pos = j * 32 + lane;

@@ -367,7 +367,10 @@ inline int umma_search(UmmaIndexState& st, Umma2IndexState& st2, const void* row
     err = "K2: shared memory plan does not fit";
     return MMR_ERR_UNSUPPORTED;
   }
-  static bool attr_set = false;
+  static bool attr_done[64] = {};
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& attr_set = attr_done[cur_dev & 63];
   if (!attr_set) {
     cudaFuncSetAttribute(scan_umma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_LIMIT);
     cudaFuncSetAttribute(scan_umma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_LIMIT);

@@ -74,6 +74,25 @@ struct WarpTopK {
     return thr;
   }
 
+  // Merge `count` candidates fetched through `key_at(i)` (returns 0 for "no key").  Loads are issued U at a time per
+  // lane before any of them is consumed, so a merge over memory costs count / (32 U) round trips, not count / 32.
+  template <int U, typename F>
+  __device__ __forceinline__ uint64_t merge_batched(F key_at, int count, uint64_t thr, int k, int lane) {
+    for (int i0 = 0; i0 < count; i0 += 32 * U) {
+      uint64_t c[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * 32 + lane;
+        c[u] = i < count ? key_at(i) : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (i0 + u * 32 < count) thr = offer(c[u], c[u] != 0ull, thr, k, lane);
+      }
+    }
+    return thr;
+  }
+
   // Write the first k positions to dst[0..k).
   __device__ __forceinline__ void store(uint64_t* dst, int k, int lane) const {
 #pragma unroll

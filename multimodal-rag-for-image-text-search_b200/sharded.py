@@ -67,23 +67,6 @@ def gather_wire(wire: Wire, gathered: GatheredWire, group=None) -> None:
     dist.all_gather_into_tensor(gathered.buf.view(-1), wire.buf, group=group)
 
 
-def merge_gathered_numpy(gathered: GatheredWire) -> Tuple[np.ndarray, np.ndarray]:
-    """Host statement of the K4 merge for the CPU tests of the exchange logic (NOT a product path)."""
-    scores, rows = gathered.views()
-    w = gathered.wire
-    s = scores.cpu().numpy().reshape(gathered.world, w.b, w.k)
-    r = rows.cpu().numpy().reshape(gathered.world, w.b, w.k)
-    out_s = np.full((w.b, w.k), -np.inf, np.float32)
-    out_r = np.full((w.b, w.k), -1, np.int64)
-    for q in range(w.b):
-        cs, cr = s[:, q].reshape(-1), r[:, q].reshape(-1)
-        keep = cr >= 0
-        cs, cr = cs[keep], cr[keep]
-        order = np.lexsort((cr, -cs.astype(np.float64)))[: w.k]
-        out_s[q, : len(order)], out_r[q, : len(order)] = cs[order], cr[order]
-    return out_s, out_r
-
-
 class PeerExchange:
     """Symmetric buffers for the fused exchange (mmr_search_exchange): one buffer per rank, mapped into every
     process with torch's symmetric memory (CUDA VMM handles over the process-group store; NVLink peer access).

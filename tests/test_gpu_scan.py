@@ -205,3 +205,28 @@ def test_loader_normalises_like_the_reference(mmr):
     ix2 = mmr.ResidentIndex.from_f32(torch.from_numpy(raw).cuda(), dtype="bf16", normalize=True)
     assert np.abs(ix2.rows.float().cpu().numpy() - ofs.bf16_round(want)).max() < 2 ** -8
     ix.close(); ix2.close()
+
+
+def test_pipelined_launches_give_identical_results(mmr, monkeypatch):
+    """MMR_PDL=1: back-to-back searches overlap (programmatic dependent launch); every result must equal the
+    serialized launch's."""
+    rows = util.unit_rows(400_000, 512, seed=101)
+    ix = mmr.ResidentIndex.from_f32(rows, dtype="bf16")
+    qs = torch.from_numpy(util.queries(64, 512)).cuda()
+    torch.cuda.synchronize()
+    results = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("MMR_PDL", mode)
+        outs = [(torch.empty((1, 10), dtype=torch.float32, device="cuda"), torch.empty((1, 10), dtype=torch.int64, device="cuda"))
+                for _ in range(64)]
+        for rep in range(3):
+            for i in range(64):
+                ix.search(qs[i:i + 1], 10, out=outs[i])
+        torch.cuda.synchronize()
+        results[mode] = (torch.cat([o[0] for o in outs]).cpu(), torch.cat([o[1] for o in outs]).cpu())
+    assert torch.equal(results["0"][1], results["1"][1])
+    assert torch.equal(results["0"][0], results["1"][0])
+    for i in (0, 17, 63):
+        util.check_topk(results["1"][0][i].numpy(), results["1"][1][i].numpy(), util.oracle_scores(rows, qs[i].cpu().numpy()),
+                        10, util.TOL_BF16, what=f"pdl q{i}")
+    ix.close()

@@ -112,3 +112,29 @@ def test_fp16_rows_on_tensor_cores(mmr):
     for j in range(7):
         util.check_topk(s[j].cpu().numpy(), r[j].cpu().numpy(), util.oracle_scores(rows, q[j]), 10, util.TOL_BF16, what=f"f16 q{j}")
     ix.close()
+
+
+@pytest.mark.parametrize("n", [1, 7, 129, 1000, 4097])
+def test_k2_on_tiny_ranges(mmr, n):
+    """The kernel family depends on the batch size only, so a 1-row tenant queried by 5 requests also runs on the
+    tensor cores: partial tiles, fewer rows than k, TMA boxes hanging over the end of the table."""
+    rows = util.unit_rows(n, 512, seed=95)
+    ix = mmr.ResidentIndex.from_f32(rows, dtype="bf16")
+    q = util.queries(5, 512)
+    s, r = ix.search(torch.from_numpy(q).cuda(), 10)
+    assert mmr._native.lib().mmr_last_kernel() == 2
+    for j in range(5):
+        util.check_topk(s[j].cpu().numpy(), r[j].cpu().numpy(), util.oracle_scores(rows, q[j]), 10, util.TOL_BF16, what=f"tiny n{n} q{j}")
+    ix.close()
+
+
+def test_k2_large_batch_parity(mmr):
+    """B = 1024 (8 query tiles, query tile in tensor memory, probe floor): a sample of queries against the oracle."""
+    rows = util.unit_rows(300_000, 512, seed=96, cone=0.3)
+    ix = mmr.ResidentIndex.from_f32(rows, dtype="bf16")
+    q = util.queries(1024, 512, cone=0.3)
+    s, r = ix.search(torch.from_numpy(q).cuda(), 10)
+    s, r = s.cpu().numpy(), r.cpu().numpy()
+    for j in list(range(0, 1024, 37)) + [127, 128, 1023]:
+        util.check_topk(s[j], r[j], util.oracle_scores(rows, q[j]), 10, util.TOL_BF16, what=f"B1024 q{j}")
+    ix.close()

@@ -17,6 +17,24 @@ from tests import util
 PKG = "multimodal-rag-for-image-text-search_b200"
 
 
+def merge_gathered_numpy(gathered):
+    """Host statement of the K4 merge, used only here to check the exchange logic on CPU (the product merges with
+    the CUDA kernel mmr_merge_topk_strided)."""
+    scores, rows = gathered.views()
+    w = gathered.wire
+    s = scores.cpu().numpy().reshape(gathered.world, w.b, w.k)
+    r = rows.cpu().numpy().reshape(gathered.world, w.b, w.k)
+    out_s = np.full((w.b, w.k), -np.inf, np.float32)
+    out_r = np.full((w.b, w.k), -1, np.int64)
+    for q in range(w.b):
+        cs, cr = s[:, q].reshape(-1), r[:, q].reshape(-1)
+        keep = cr >= 0
+        cs, cr = cs[keep], cr[keep]
+        order = np.lexsort((cr, -cs.astype(np.float64)))[: w.k]
+        out_s[q, : len(order)], out_r[q, : len(order)] = cs[order], cr[order]
+    return out_s, out_r
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -47,7 +65,7 @@ def _worker(rank, world, port, n_rows, dim, b, k, ret):
             wire.scores[q, :len(ids)] = torch.from_numpy((np.float32(1) - dist_all[q, lo:hi][ids]).astype(np.float32))
             wire.rows[q, :len(ids)] = torch.from_numpy(ids + lo)
         sh.gather_wire(wire, gathered)
-        s, r = sh.merge_gathered_numpy(gathered)
+        s, r = merge_gathered_numpy(gathered)
         if rank == 0:
             ret["bounds"] = bounds
             ret["scores"], ret["rows"] = s, r
