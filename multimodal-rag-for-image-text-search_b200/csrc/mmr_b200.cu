@@ -523,16 +523,20 @@ extern "C" int mmr_search_ranges(const mmr_index* ix, const float* queries_dev, 
   return search_varlen_stream(ix, queries_dev, per_query, k, out_scores_dev, out_rows_dev, ws, workspace_bytes, st);
 }
 
+// Result staging is ONE buffer on each side ([scores f32 B*k | pad | rows i64 B*k]) so a search costs one D2H copy.
+static size_t staging_rows_off(int cb, int ck) { return align_up(size_t(cb) * ck * 4, 16); }
+
 static int ensure_staging(mmr_index* ix, int B, int k) {
   if (B <= ix->cap_b && k <= ix->cap_k) return MMR_OK;
   free_staging(ix);
   const int cb = std::max(B, 8), ck = std::max(k, 16);
+  const size_t res_bytes = staging_rows_off(cb, ck) + size_t(cb) * ck * 8;
   CUDA_TRY(cudaMallocHost(&ix->h_q, size_t(cb) * ix->dim * 4));
-  CUDA_TRY(cudaMallocHost(&ix->h_scores, size_t(cb) * ck * 4));
-  CUDA_TRY(cudaMallocHost(&ix->h_rows, size_t(cb) * ck * 8));
+  CUDA_TRY(cudaMallocHost(&ix->h_scores, res_bytes));
   CUDA_TRY(cudaMalloc(&ix->d_q, size_t(cb) * ix->dim * 4));
-  CUDA_TRY(cudaMalloc(&ix->d_scores, size_t(cb) * ck * 4));
-  CUDA_TRY(cudaMalloc(&ix->d_rows, size_t(cb) * ck * 8));
+  CUDA_TRY(cudaMalloc(&ix->d_scores, res_bytes));
+  ix->h_rows = nullptr;  // views into the packed buffers are computed per call (they depend on B and k)
+  ix->d_rows = nullptr;
   ix->ws_bytes = mmr_search_workspace_bytes(ix, cb, ck);
   CUDA_TRY(cudaMalloc(&ix->d_ws, ix->ws_bytes));
   CUDA_TRY(cudaMemset(ix->d_ws, 0, ix->ws_bytes));
@@ -551,15 +555,19 @@ extern "C" int mmr_search_host(mmr_index* ix, const float* queries_host, const i
   int rc = ensure_staging(ix, B, k);
   if (rc != MMR_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t rows_off = staging_rows_off(B, k);
+  const size_t res_bytes = rows_off + size_t(B) * k * 8;
+  uint8_t* d_res = reinterpret_cast<uint8_t*>(ix->d_scores);
+  uint8_t* h_res = reinterpret_cast<uint8_t*>(ix->h_scores);
   memcpy(ix->h_q, queries_host, size_t(B) * ix->dim * 4);
   CUDA_TRY(cudaMemcpyAsync(ix->d_q, ix->h_q, size_t(B) * ix->dim * 4, cudaMemcpyHostToDevice, st));
-  rc = mmr_search(ix, ix->d_q, query_seg_host, B, k, ix->d_scores, ix->d_rows, ix->d_ws, ix->ws_bytes, st);
+  rc = mmr_search(ix, ix->d_q, query_seg_host, B, k, reinterpret_cast<float*>(d_res),
+                  reinterpret_cast<int64_t*>(d_res + rows_off), ix->d_ws, ix->ws_bytes, st);
   if (rc != MMR_OK) return rc;
-  CUDA_TRY(cudaMemcpyAsync(ix->h_scores, ix->d_scores, size_t(B) * k * 4, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(ix->h_rows, ix->d_rows, size_t(B) * k * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(h_res, d_res, res_bytes, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
-  memcpy(out_scores_host, ix->h_scores, size_t(B) * k * 4);
-  memcpy(out_rows_host, ix->h_rows, size_t(B) * k * 8);
+  memcpy(out_scores_host, h_res, size_t(B) * k * 4);
+  memcpy(out_rows_host, h_res + rows_off, size_t(B) * k * 8);
   return MMR_OK;
 }
 

@@ -315,7 +315,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1) scan_stream_kernel(const Stream
       WarpTopK<KPL> m;
       m.clear();
       uint64_t t = 0ull;
-      for (int w = 0; w < K1_NW; ++w) t = m.merge_from(wk + (w * NQ + qi) * C::KSLOTS, k, 1, t, k, lane);
+      // all heads first (position-major over the NW warp lists), so most later candidates fail the ballot
+      t = m.template merge_batched<4>(
+          [&](int i) -> uint64_t { return wk[((i % K1_NW) * NQ + qi) * C::KSLOTS + i / K1_NW]; }, K1_NW * k, t, k, lane);
       m.store(p.partial + (size_t(blockIdx.x) * NQ + qi) * k, k, lane);
     }
     // grid-level merge by the last CTA to arrive
@@ -353,7 +355,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) scan_stream_kernel(const Stream
         WarpTopK<KPL> f;
         f.clear();
         uint64_t tf = 0ull;
-        for (int w = 0; w < K1_NW; ++w) tf = f.merge_from(wk + w * C::KSLOTS, k, 1, tf, k, lane);
+        tf = f.template merge_batched<4>(
+            [&](int i) -> uint64_t { return wk[(i % K1_NW) * C::KSLOTS + i / K1_NW]; }, K1_NW * k, tf, k, lane);
 #pragma unroll
         for (int j = 0; j < KPL; ++j) {
           const int pos = j * 32 + lane;

@@ -85,10 +85,15 @@ def _prepare_metadata(chunk) -> Dict[str, Any]:
 
 
 def _join(raw: List[Dict[str, Any]], modality: str, need_text: bool) -> List[Dict[str, Any]]:
-    """Per-hit metadata join and drop rules (retrieve.py:55-67 / 86-98)."""
+    """Per-hit metadata join and drop rules (retrieve.py:55-67 / 86-98).
+
+    The reference issues one SELECT per hit (N+1); a metadata store that offers
+    `get_chunks(ids) -> {id: chunk}` is asked once per result list instead."""
     out = []
+    bulk = getattr(_METADATA_STORE, "get_chunks", None)
+    found = bulk([hit["chunk_id"] for hit in raw]) if (bulk and raw) else None
     for hit in raw:
-        chunk = _METADATA_STORE.get_chunk(hit["chunk_id"])
+        chunk = found.get(hit["chunk_id"]) if found is not None else _METADATA_STORE.get_chunk(hit["chunk_id"])
         if not chunk or (need_text and not chunk.text):
             continue
         out.append({

@@ -184,3 +184,22 @@ def test_version_file(tmp_path):
     assert json.load(open(tmp_path / "lance" / "index_versions.json")) == {"u": 2, "v": 1}
     mem = versions.VersionFile(None)
     assert mem.bump("x") == 1 and mem.get("x") == 1
+
+
+def test_batched_metadata_join_is_used_when_offered(monkeypatch):
+    text_rows = [{"chunk_id": c, "score": s, "meta": {}} for c, s in (("a", .9), ("gone", .8), ("b", .6))]
+    chunks = {"a": Chunk("a", "d", "text", text="x"), "b": Chunk("b", "d", "text", text="y")}
+    calls = {"bulk": 0, "single": 0}
+
+    class Meta:
+        def get_chunks(self, ids):
+            calls["bulk"] += 1
+            return {i: chunks[i] for i in ids if i in chunks}
+
+        def get_chunk(self, cid):
+            calls["single"] += 1
+            return chunks.get(cid)
+
+    _wire(monkeypatch, DummyStore(text_rows, []), Meta(), False)
+    got = retrieve.retrieve_text("u", "q")
+    assert [g["chunk_id"] for g in got] == ["a", "b"] and calls == {"bulk": 1, "single": 0}
