@@ -231,6 +231,22 @@ class _Collection:
         return self._resident
 
     # -- reads --------------------------------------------------------------------------------
+    def search_device(self, user_ids: Sequence[str], vectors: np.ndarray, top_k: int):
+        """Batched search that leaves the results on the device: (scores [B,k] f32, rows [B,k] i64) with -1 rows for
+        unknown tenants, or None when the collection is empty."""
+        limit = max(int(top_k), 1)
+        if limit > N.MMR_MAX_K:
+            raise N.NativeError(f"top_k {limit} > {N.MMR_MAX_K}: not supported by the resident-index kernels")
+        res = self.resident()
+        if res is None:
+            return None
+        ranges = [self._ranges.get(str(u)) or [] for u in user_ids]
+        q = torch.from_numpy(np.ascontiguousarray(vectors, dtype=np.float32)).to(self.device)
+        return res.search_ranges(q, limit, ranges)
+
+    def row_identity(self, resident_row: int) -> int:
+        return int(self._perm[resident_row])
+
     def search(self, user_ids: Sequence[str], vectors: np.ndarray, top_k: int) -> List[List[Dict[str, Any]]]:
         limit = max(int(top_k), 1)
         if limit > N.MMR_MAX_K:
@@ -327,6 +343,39 @@ class B200Store:
 
     def search_image_batch(self, user_ids: Sequence[str], query_vecs, top_k: int) -> List[List[Dict[str, Any]]]:
         return self._image_table.search(list(user_ids), np.asarray(query_vecs, dtype=np.float32), top_k)
+
+    def fused_search_batch(self, user_ids: Sequence[str], text_vecs, image_vecs, top_k_text: int, top_k_image: int,
+                           final_n: int, tau: float):
+        """Rerank-off request path kept on the device: text scan + image scan + z-score fusion + FINAL_N cut +
+        CONFIDENCE_TAU gate (kernels K1/K2 + K5).  Returns per request ([{"chunk_id", "modality", "score",
+        "combined_score"}, ...] best first, low_confidence flag) -- what retrieve() then _confidence_low() give when
+        every hit survives the metadata join (reference app/ml/retrieve.py:103-117, app/ml/generate.py:56-60)."""
+        return _fused_batch(self, list(user_ids), text_vecs, image_vecs, top_k_text, top_k_image, final_n, tau)
+
+
+def _fused_batch(store: "B200Store", user_ids, text_vecs, image_vecs, kt: int, ki: int, final_n: int, tau: float):
+    """scan(text) + scan(image) + K5 fusion/gate for a batch of requests, results fetched with one small D2H."""
+    from .index import fuse
+
+    t = store._text_table.search_device(user_ids, np.asarray(text_vecs, dtype=np.float32), kt)
+    i = store._image_table.search_device(user_ids, np.asarray(image_vecs, dtype=np.float32), ki)
+    if t is None and i is None:
+        return [([], True) for _ in user_ids]
+    out = fuse(t, i, final_n, tau)
+    comb, score = out["combined"].cpu().numpy(), out["score"].cpu().numpy()
+    rows, mod, low = out["rows"].cpu().numpy(), out["modality"].cpu().numpy(), out["low_conf"].cpu().numpy()
+    results = []
+    for b in range(len(user_ids)):
+        items = []
+        for o in range(final_n):
+            if rows[b, o] < 0:
+                break
+            coll = store._text_table if mod[b, o] == 0 else store._image_table
+            h = coll.row_identity(int(rows[b, o]))
+            items.append({"chunk_id": coll.chunk_id[h], "modality": "text" if mod[b, o] == 0 else "image",
+                          "score": float(score[b, o]), "combined_score": float(comb[b, o])})
+        results.append((items, bool(low[b])))
+    return results
 
 
 def make_arrow_table(chunk_ids, user_ids, document_ids, modalities, embeddings: np.ndarray, metas):

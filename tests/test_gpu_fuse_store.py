@@ -233,3 +233,50 @@ def test_incremental_upserts_track_the_oracle_store(mmr):
         check(f"compaction{step}")
     assert coll.rebuilds >= 2 and coll._tomb == 0
     assert gpu.get_index_version("a") >= 10
+
+
+def test_retrieve_batch_device_equals_host_retrieve(mmr):
+    """B concurrent requests: device path (two batched scans + K5) == per-request host path (retrieve + gate),
+    bit for bit on combined scores, same winners, same gate; a winner that fails the join falls back to the host path."""
+    retrieve = importlib.import_module(PKG + ".retrieve")
+    cache = importlib.import_module(PKG + ".cache")
+    settings_mod = importlib.import_module(PKG + ".settings")
+    cache.clear_all_caches()
+    n_t, n_i = 6000, 2500
+    temb, iemb = util.unit_rows(n_t, 384, 15), util.unit_rows(n_i, 512, 16)
+    users = ["u0", "u1", "u2"]
+    store = mmr.B200Store()
+    store.load_arrow("text_collection", mmr.make_arrow_table([f"t{i}" for i in range(n_t)], [users[i % 3] for i in range(n_t)],
+                                                             ["d"] * n_t, ["text"] * n_t, temb, ["{}"] * n_t))
+    store.load_arrow("image_collection", mmr.make_arrow_table([f"i{i}" for i in range(n_i)], [users[i % 3] for i in range(n_i)],
+                                                              ["d"] * n_i, ["image"] * n_i, iemb, ["{}"] * n_i))
+    chunks = {f"t{i}": SimpleNamespace(id=f"t{i}", document_id="d", modality="text", text=f"text {i}", meta={},
+                                       page_no=i, start_ts=None, end_ts=None, file_path=None) for i in range(n_t)}
+    chunks.update({f"i{i}": SimpleNamespace(id=f"i{i}", document_id="d", modality="image", text=None, meta={},
+                                            page_no=None, start_ts=None, end_ts=None, file_path=f"/f/{i}.jpg") for i in range(n_i)})
+    qtext = {f"query {j}": util.queries(1, 384, seed=100 + j)[0] for j in range(9)}
+    qimg = {f"query {j}": util.queries(1, 512, seed=200 + j)[0] for j in range(9)}
+    retrieve.configure(store=store, metadata=SimpleNamespace(get_chunk=chunks.get),
+                       text_encoder=lambda texts: qtext[texts[0]][None, :], image_query_encoder=lambda q: qimg[q],
+                       retrieval_settings=settings_mod.RetrievalSettings(use_rerank=False))
+    reqs = [(users[j % 3], f"query {j}") for j in range(9)] + [("nobody", "query 0")]
+    dev = retrieve.retrieve_batch_device([u for u, _ in reqs], [q for _, q in reqs])
+    for (u, q), (items, low) in zip(reqs, dev):
+        cache.clear_all_caches()
+        host = retrieve.retrieve(u, q)
+        assert [it["chunk_id"] for it in items] == [h["chunk_id"] for h in host], (u, q)
+        assert [it["combined_score"] for it in items] == [h["combined_score"] for h in host]
+        assert [it["score"] for it in items] == [h["score"] for h in host]
+        assert [it["metadata"] for it in items] == [h["metadata"] for h in host]
+        assert low is retrieve._confidence_low(host)
+    # knock out one winner's chunk: the device result cannot be trusted for that request -> host path result
+    victim = dev[0][0][0]["chunk_id"]
+    gone = dict(chunks)
+    del gone[victim]
+    retrieve.configure(metadata=SimpleNamespace(get_chunk=gone.get))
+    cache.clear_all_caches()
+    again = retrieve.retrieve_batch_device([reqs[0][0]], [reqs[0][1]])
+    cache.clear_all_caches()
+    assert [it["chunk_id"] for it in again[0][0]] == [h["chunk_id"] for h in retrieve.retrieve(*reqs[0])]
+    assert victim not in [it["chunk_id"] for it in again[0][0]]
+    cache.clear_all_caches()
