@@ -128,6 +128,28 @@ __device__ __forceinline__ void lds_v4(uint32_t addr, uint32_t (&r)[4]) {
 __device__ __forceinline__ void lds_v2(uint32_t addr, uint32_t (&r)[2]) {
   asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
 }
+// Programmatic dependent launch, the always-safe form: the kernel lets its successor be scheduled right away and
+// itself waits for its predecessor's completion (and memory flush) before doing anything.  Only launch latency and
+// per-CTA setup overlap; data dependencies are untouched.
+__device__ __forceinline__ void pdl_chain_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 #endif  // __CUDACC__
 
 }  // namespace mmr

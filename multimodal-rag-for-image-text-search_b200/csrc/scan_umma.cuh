@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
 scan_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x,
                  const UmmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_chain_prologue();
   constexpr int NACC = TS ? 2 : K2_ACC;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -439,6 +440,7 @@ template <int KPL>
 __global__ void merge_partials_kernel(const uint64_t* __restrict__ partial, int n_qtiles, int n_rslots, int B, int k,
                                       float* __restrict__ out_scores, int64_t* __restrict__ out_rows,
                                       int64_t row_base) {
+  pdl_chain_prologue();
   const int lane = threadIdx.x & 31;
   const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= B) return;
@@ -469,6 +471,7 @@ __global__ void merge_partials_kernel(const uint64_t* __restrict__ partial, int 
 template <int KPL>
 __global__ void probe_floor_kernel(const float* __restrict__ probe, int n_qtiles, int n_rslots, int B, int k,
                                    float* __restrict__ floor) {
+  pdl_chain_prologue();
   const int lane = threadIdx.x & 31;
   const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= B) return;
@@ -488,6 +491,7 @@ __global__ void probe_floor_kernel(const float* __restrict__ probe, int n_qtiles
 // fp32 queries -> L2-normalised bf16 (LanceDBStore._normalize, then narrowed for the tensor cores). Warp per query.
 template <typename E>
 __global__ void prep_queries_kernel(const float* __restrict__ q, E* __restrict__ out, int B, int dim) {
+  pdl_chain_prologue();
   const int lane = threadIdx.x & 31;
   const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (qi >= B) return;

@@ -87,6 +87,7 @@ template <bool DUMP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(K2_THREADS, 1)
 scan_umma2_kernel(const __grid_constant__ CUtensorMap tm_x, const UmmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_chain_prologue();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int ks = p.ks, nstages = p.nstages, k = p.k;
@@ -403,8 +404,8 @@ inline int umma_search(UmmaIndexState& st, Umma2IndexState& st2, const void* row
   float* probe = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(partial) + umma_align(size_t(ctas_max) * K2_BM * k * 8));
   float* floor = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(probe) + umma_align(size_t(ctas_max) * K2_BM * 4));
   const char* noprobe = getenv("MMR_UMMA_NOPROBE");
-  if (dtype == MMR_BF16) prep_queries_kernel<__nv_bfloat16><<<(B + 3) / 4, 128, 0, stream>>>(queries, qb, B, dim);
-  else prep_queries_kernel<__half><<<(B + 3) / 4, 128, 0, stream>>>(queries, reinterpret_cast<__half*>(qb), B, dim);
+  if (dtype == MMR_BF16) launch_pdl(prep_queries_kernel<__nv_bfloat16>, dim3((B + 3) / 4), dim3(128), 0, stream, queries, qb, B, dim);
+  else launch_pdl(prep_queries_kernel<__half>, dim3((B + 3) / 4), dim3(128), 0, stream, queries, reinterpret_cast<__half*>(qb), B, dim);
   const int max_q_per_pass = sm_count * K2_BM;
   for (int q0 = 0; q0 < B; q0 += max_q_per_pass) {
     const int bq = std::min(B - q0, max_q_per_pass);
@@ -442,31 +443,29 @@ inline int umma_search(UmmaIndexState& st, Umma2IndexState& st2, const void* row
       UmmaParams pp = p;
       pp.probe_out = probe;
       pp.probe_tiles = int(std::max<int64_t>(1, std::min<int64_t>(16, tiles_per_cta / 24)));
-      if (pair) scan_umma2_kernel<false><<<grid, K2_THREADS, smem2_bytes, stream>>>(st2.map, pp);
-      else if (ts) scan_umma_kernel<false, true><<<grid, K2_THREADS, smem_bytes, stream>>>(tm_q, st.map, pp);
-      else scan_umma_kernel<false, false><<<grid, K2_THREADS, smem_bytes, stream>>>(tm_q, st.map, pp);
+      if (pair) launch_pdl(scan_umma2_kernel<false>, dim3(grid), dim3(K2_THREADS), smem2_bytes, stream, st2.map, pp);
+      else if (ts) launch_pdl(scan_umma_kernel<false, true>, dim3(grid), dim3(K2_THREADS), smem_bytes, stream, tm_q, st.map, pp);
+      else launch_pdl(scan_umma_kernel<false, false>, dim3(grid), dim3(K2_THREADS), smem_bytes, stream, tm_q, st.map, pp);
       const int wpb = 4;
-      if (k <= 32) probe_floor_kernel<1><<<(bq + wpb - 1) / wpb, wpb * 32, 0, stream>>>(probe, p.n_qtiles, p.n_rslots, bq, k, floor + q0);
-      else probe_floor_kernel<2><<<(bq + wpb - 1) / wpb, wpb * 32, 0, stream>>>(probe, p.n_qtiles, p.n_rslots, bq, k, floor + q0);
+      if (k <= 32) launch_pdl(probe_floor_kernel<1>, dim3((bq + wpb - 1) / wpb), dim3(wpb * 32), 0, stream, probe, p.n_qtiles, p.n_rslots, bq, k, floor + q0);
+      else launch_pdl(probe_floor_kernel<2>, dim3((bq + wpb - 1) / wpb), dim3(wpb * 32), 0, stream, probe, p.n_qtiles, p.n_rslots, bq, k, floor + q0);
       p.floor = floor + q0;
     }
     if (dump) {
-      if (pair) scan_umma2_kernel<true><<<grid, K2_THREADS, smem2_bytes, stream>>>(st2.map, p);
-      else if (ts) scan_umma_kernel<true, true><<<grid, K2_THREADS, smem_bytes, stream>>>(tm_q, st.map, p);
-      else scan_umma_kernel<true, false><<<grid, K2_THREADS, smem_bytes, stream>>>(tm_q, st.map, p);
+      if (pair) launch_pdl(scan_umma2_kernel<true>, dim3(grid), dim3(K2_THREADS), smem2_bytes, stream, st2.map, p);
+      else if (ts) launch_pdl(scan_umma_kernel<true, true>, dim3(grid), dim3(K2_THREADS), smem_bytes, stream, tm_q, st.map, p);
+      else launch_pdl(scan_umma_kernel<true, false>, dim3(grid), dim3(K2_THREADS), smem_bytes, stream, tm_q, st.map, p);
     } else {
-      if (pair) scan_umma2_kernel<false><<<grid, K2_THREADS, smem2_bytes, stream>>>(st2.map, p);
-      else if (ts) scan_umma_kernel<false, true><<<grid, K2_THREADS, smem_bytes, stream>>>(tm_q, st.map, p);
-      else scan_umma_kernel<false, false><<<grid, K2_THREADS, smem_bytes, stream>>>(tm_q, st.map, p);
+      if (pair) launch_pdl(scan_umma2_kernel<false>, dim3(grid), dim3(K2_THREADS), smem2_bytes, stream, st2.map, p);
+      else if (ts) launch_pdl(scan_umma_kernel<false, true>, dim3(grid), dim3(K2_THREADS), smem_bytes, stream, tm_q, st.map, p);
+      else launch_pdl(scan_umma_kernel<false, false>, dim3(grid), dim3(K2_THREADS), smem_bytes, stream, tm_q, st.map, p);
       const int wpb = 4;
       if (k <= 32)
-        merge_partials_kernel<1><<<(bq + wpb - 1) / wpb, wpb * 32, 0, stream>>>(partial, p.n_qtiles, p.n_rslots, bq, k,
-                                                                              out_s + size_t(q0) * k,
-                                                                              out_r + size_t(q0) * k, row_base);
+        launch_pdl(merge_partials_kernel<1>, dim3((bq + wpb - 1) / wpb), dim3(wpb * 32), 0, stream, partial, p.n_qtiles,
+                   p.n_rslots, bq, k, out_s + size_t(q0) * k, out_r + size_t(q0) * k, row_base);
       else
-        merge_partials_kernel<2><<<(bq + wpb - 1) / wpb, wpb * 32, 0, stream>>>(partial, p.n_qtiles, p.n_rslots, bq, k,
-                                                                              out_s + size_t(q0) * k,
-                                                                              out_r + size_t(q0) * k, row_base);
+        launch_pdl(merge_partials_kernel<2>, dim3((bq + wpb - 1) / wpb), dim3(wpb * 32), 0, stream, partial, p.n_qtiles,
+                   p.n_rslots, bq, k, out_s + size_t(q0) * k, out_r + size_t(q0) * k, row_base);
     }
   }
   cudaError_t e = cudaGetLastError();
