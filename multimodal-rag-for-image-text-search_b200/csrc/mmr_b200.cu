@@ -648,14 +648,27 @@ extern "C" int mmr_search_exchange(const mmr_index* ix, const float* queries_dev
   const uint8_t* local = reinterpret_cast<const uint8_t*>(peer_bufs_host[rank]);
   const int wpb = 4;
   const uint64_t timeout_ns = 5000000000ull;
+  // With MMR_PDL=1 the wait+merge kernel is a programmatic dependent of the scan: it may become resident while the scan
+  // still runs (it only spins on the flags, which the scan's last CTA releases at its very end) and the next search's
+  // scan may in turn start behind it.  Otherwise plain stream order.
+  const char* pdl = getenv("MMR_PDL");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((B + wpb - 1) / wpb);
+  cfg.blockDim = dim3(wpb * 32);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = (pushed && pdl && pdl[0] == '1') ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   if (k <= 32)
-    merge_wait_kernel<1><<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(local, parity, seq, wire_bytes, score_bytes, G, B, k,
-                                                                 out_scores_dev, out_rows_dev, timeout_ns);
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, merge_wait_kernel<1>, local, parity, seq, wire_bytes, score_bytes, int(G), int(B),
+                                int(k), out_scores_dev, out_rows_dev, timeout_ns));
   else
-    merge_wait_kernel<2><<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(local, parity, seq, wire_bytes, score_bytes, G, B, k,
-                                                                 out_scores_dev, out_rows_dev, timeout_ns);
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, merge_wait_kernel<2>, local, parity, seq, wire_bytes, score_bytes, int(G), int(B),
+                                int(k), out_scores_dev, out_rows_dev, timeout_ns));
   g_launches++;
-  CUDA_TRY(cudaGetLastError());
   return MMR_OK;
 }
 

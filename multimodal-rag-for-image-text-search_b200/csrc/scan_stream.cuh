@@ -375,13 +375,14 @@ __global__ void __launch_bounds__(K1_THREADS, 1) scan_stream_kernel(const Stream
         }
       }
     }
+    if (threadIdx.x == 0) *p.ticket = 0u;  // ready for the next launch (before the flags: a pipelined successor
+                                           // may pass its dependency wait as soon as the exchange completes)
     if (p.n_peers > 0) {
       __threadfence_system();
       __syncthreads();
       if (int(threadIdx.x) < p.n_peers)
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.peer_flag[threadIdx.x]), "r"(p.seq) : "memory");
     }
-    if (threadIdx.x == 0) *p.ticket = 0u;  // ready for the next launch
   } else {
     // ------------------------------ varlen mode (NQ == 1) ------------------------------
     // item i -> global warp (i mod total_warps); each item is one (query, row range); the partial of

@@ -37,12 +37,13 @@ def _worker(rank, world, port, ret):
         local = pkg.ResidentIndex(full_dev[lo:hi].contiguous(), row_base=lo)
         single = pkg.ResidentIndex(full_dev)
         results = {}
-        for mode in ("nccl", "fused"):
-            sh = pkg.ShardedIndex(local, exchange=mode)
+        for mode in ("nccl", "fused", "fused-pipelined"):
+            os.environ["MMR_PDL"] = "1" if mode == "fused-pipelined" else "0"
+            sh = pkg.ShardedIndex(local, exchange="fused" if mode.startswith("fused") else "nccl")
             for b, k in ((1, 10), (2, 12), (5, 10), (130, 50)):
                 qs = np.concatenate([util.queries(b - 1, 512, seed=b), rows[11:12]]) if b > 1 else rows[11:12].copy()
                 qd = torch.from_numpy(qs).cuda()
-                for rep in range(3):                            # sequence numbers / slot parity roll over
+                for rep in range(3 if mode != "fused-pipelined" else 40):  # sequence numbers / slot parity roll over
                     s, r = sh.search(qd, k)
                 torch.cuda.synchronize()
                 s1, r1 = single.search(qd, k)
@@ -51,7 +52,7 @@ def _worker(rank, world, port, ret):
                 assert r[-1, 0].item() == 11 and r[-1, 1].item() == n - 5
                 results[(mode, b, k)] = r.cpu()
         for (mode, b, k), r in results.items():
-            if mode == "fused":
+            if mode != "nccl":
                 assert torch.equal(r, results[("nccl", b, k)])
         if rank == 0:
             ret["ok"] = True
