@@ -88,6 +88,7 @@ class _Collection:
         self._pending_rows: List[int] = []         # host rows not yet resident
         self._pending_tomb: List[int] = []         # resident rows to overwrite with NaN
         self._force_rebuild = True
+        self._seg_key = None
         self.rebuilds = 0
         self.appends = 0
 
@@ -173,6 +174,7 @@ class _Collection:
         self._n_res = n
         self._resident = ResidentIndex(self._buf[:n])
         self._resident.update(self._buf, n)
+        self._seg_key = None
         self._res_of = {int(h): i for i, h in enumerate(self._perm)}
         self._ranges = {str(u): [[int(seg[i]), int(seg[i + 1])]] for i, u in enumerate(uniq)}
         self.rebuilds += 1
@@ -213,6 +215,7 @@ class _Collection:
             self._n_res = lo + m
             self.appends += 1
         self._resident.update(self._buf, self._n_res)
+        self._seg_key = None
 
     def resident(self) -> Optional[ResidentIndex]:
         if not self._force_rebuild and not self._pending_rows and not self._pending_tomb:
@@ -263,7 +266,9 @@ class _Collection:
         if all(len(ranges[i]) == 1 and ranges[i] == ranges[live[0]] for i in live):
             # one shared range: host-buffer C call (H2D + scan + D2H inside the library)
             lo, hi = ranges[live[0]][0]
-            res.update(self._buf, self._n_res, seg_offsets=[lo, hi])
+            if self._seg_key != (lo, hi, self._n_res):          # re-point the one-segment table only when it changes
+                res.update(self._buf, self._n_res, seg_offsets=[lo, hi])
+                self._seg_key = (lo, hi, self._n_res)
             scores, rows = res.search_host(q, limit, [0] * len(live))
         else:
             s_dev, r_dev = res.search_ranges(torch.from_numpy(q).to(self.device), limit, [ranges[i] for i in live])
