@@ -575,7 +575,11 @@ inline int umma_plan_stages(int dim, int k, size_t* smem_bytes, bool ts = false)
 // (same query precision, same per-row arithmetic) as the whole table and sharded results stay bit-identical.
 //   B <= 2  : K1 (fp32 queries, one launch, HBM-bound)      B >= 3, bf16/fp16 rows : K2 (16-bit queries on tcgen05)
 inline bool umma_preferred(int dtype, int dim, int B, int k, int64_t nrows) {
-  if ((dtype != MMR_BF16 && dtype != MMR_F16) || dim % 64 != 0 || B < 3) return false;
+  // MMR_FORCE_FAMILY=1|2 (measurement only, profiles/r01_k2_summary.md "crossover"): pin the family regardless of B
+  const char* force = getenv("MMR_FORCE_FAMILY");
+  const int min_b = (force && force[0] == '2') ? 1 : 3;
+  if (force && force[0] == '1') return false;
+  if ((dtype != MMR_BF16 && dtype != MMR_F16) || dim % 64 != 0 || B < min_b) return false;
   if (nrows <= 0 || nrows >= (int64_t(1) << 31)) return false;
   return umma_plan_stages(dim, k, nullptr) >= 2;
 }
