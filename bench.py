@@ -305,7 +305,8 @@ def run_b200(args):
         ix.search(q_dev[i], k, out=(out_s, out_r))
     ev3.record()
     torch.cuda.synchronize(device)
-    n_launch = (B + 3) // 4 if lib.mmr_last_kernel() == 1 else 1  # K2: the scan kernel dominates its 5 launches
+    per_pass = 8 if args.dtype == "f32" else 4
+    n_launch = (B + per_pass - 1) // per_pass if lib.mmr_last_kernel() == 1 else 1  # K2: the scan kernel dominates its 5 launches
     kernel_ms = ev2.elapsed_time(ev3) / (K * n_launch)
     hbm_peak, tf_peak, peak_kind = measured_peaks()
     algo_bytes = (hi - lo) * D * esize

@@ -272,6 +272,9 @@ static int launch_stream_ed(const StreamParams& p, int nq_pad, int kpl, int grid
 #define MMR_CASE(NQ_, KPL_) \
   if (nq_pad == NQ_ && kpl == KPL_) return launch_stream_t<E, D, NQ_, KPL_>(p, grid, st);
   MMR_CASE(1, 1) MMR_CASE(1, 2) MMR_CASE(2, 1) MMR_CASE(2, 2) MMR_CASE(4, 1) MMR_CASE(4, 2)
+  if constexpr (sizeof(E) == 4) {  // fp32 rows stream half as many rows per byte: 8 queries per pass stay HBM-bound
+    MMR_CASE(8, 1) MMR_CASE(8, 2)
+  }
 #undef MMR_CASE
   return fail(MMR_ERR_UNSUPPORTED, "no stream kernel for nq=%d kpl=%d", nq_pad, kpl);
 }
@@ -306,7 +309,7 @@ static int max_varlen_items(const mmr_index* ix, int B) { return ix->sm_count * 
 extern "C" size_t mmr_search_workspace_bytes(const mmr_index* ix, int32_t B, int32_t k) {
   if (!ix || B <= 0 || k <= 0) return 0;
   const size_t kk = size_t(std::min<int32_t>(k, MMR_MAX_K));
-  const size_t uniform = size_t(ix->sm_count) * 4 * kk * 8;
+  const size_t uniform = size_t(ix->sm_count) * 8 * kk * 8;
   const size_t items = size_t(max_varlen_items(ix, B));
   const size_t varlen = align_up(items * kk * 8, 256) + align_up(items * sizeof(ScanItem), 256) +
                         align_up(size_t(B + 1) * 4, 256);
@@ -332,9 +335,10 @@ static int search_uniform_stream(const mmr_index* ix, const float* q, int B, int
   const int R = rows_per_stage(ix->dtype);
   const int64_t nchunks = (int64_t(r1) - r0 + R - 1) / R;
   int grid = int(std::min<int64_t>(ix->sm_count, std::max<int64_t>(1, (nchunks + K1_NW - 1) / K1_NW)));
-  for (int q0 = 0; q0 < B; q0 += 4) {
-    const int nq = std::min(4, B - q0);
-    const int nq_pad = nq == 3 ? 4 : nq;
+  const int group = ix->dtype == MMR_F32 ? 8 : 4;  // queries per pass
+  for (int q0 = 0; q0 < B; q0 += group) {
+    const int nq = std::min(group, B - q0);
+    const int nq_pad = nq <= 2 ? nq : (nq <= 4 ? 4 : 8);
     StreamParams p{};
     p.rows = ix->rows;
     p.queries = q;
@@ -350,7 +354,7 @@ static int search_uniform_stream(const mmr_index* ix, const float* q, int B, int
     p.row_base = ix->row_base;
     p.items = nullptr;
     p.n_items = 0;
-    if (xi && B <= 4) {
+    if (xi && B <= group) {
       p.n_peers = xi->n_peers;
       p.seq = xi->seq;
       p.wire_score_bytes = xi->wire_score_bytes;
@@ -625,7 +629,7 @@ extern "C" int mmr_search_exchange(const mmr_index* ix, const float* queries_dev
 #ifdef MMR_WITH_UMMA
   k2 = uniform && umma_preferred(ix->dtype, ix->dim, B, k, int64_t(r1) - r0);
 #endif
-  if (uniform && !k2 && B <= 4) {
+  if (uniform && !k2 && B <= (ix->dtype == MMR_F32 ? 8 : 4)) {
     // K1 computes and pushes in ONE kernel: its last CTA stores the result into every peer over NVLink
     int rc = search_uniform_stream(ix, queries_dev, B, k, r0, r1, w_scores, w_rows, ws, st, &xi);
     if (rc != MMR_OK) return rc;
