@@ -1,5 +1,6 @@
-import importlib, sys, torch, numpy as np
-sys.path.insert(0,'/root/repo')
+"""Scan time vs table size at batch 1 (K1) and 8 (K2): the intercept of the linear fit is the fixed cost per search."""
+import importlib, os, sys, torch, numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 pkg=importlib.import_module("multimodal-rag-for-image-text-search_b200")
 dev=torch.device('cuda:0')
