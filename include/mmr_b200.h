@@ -153,6 +153,21 @@ int mmr_fuse(const float* text_scores_dev, const int64_t* text_rows_dev, int32_t
              uint8_t* out_low_conf_dev, void* stream);
 
 /*
+ * Fusion + gate, complete form: _rerank_text's re-ordering (reference app/ml/retrieve.py:150-154), _fuse_results
+ * (:158-183, including the rerank z-scores and their positional indexing), _z_scores (:186-195) and _confidence_low
+ * (app/ml/generate.py:56-60), from the float64 scores the reference's Python sees.  The cross-encoder itself stays on
+ * the host: its logits come in as text_rerank_dev, assigned to the first rerank_count[b] text items exactly as
+ * `zip(top_candidates, scores)` assigns them (rerank_count_dev NULL = rerank off).  Bit-identical to the reference's own
+ * outputs on the golden vectors (tests/golden/fusion_golden.json).
+ *   text_scores [B, kt] scan order, text_count [B]; img_scores [B, ki], img_count [B];
+ *   out_combined [B, final_n] f64; out_index [B, final_n] i32: text item j -> j, image item j -> kt + j, -1 = none.
+ */
+int mmr_fuse_f64(const double* text_scores_dev, const int32_t* text_count_dev, const double* text_rerank_dev,
+                 const int32_t* rerank_count_dev, const double* img_scores_dev, const int32_t* img_count_dev,
+                 int32_t kt, int32_t ki, int32_t B, int32_t final_n, double tau, double* out_combined_dev,
+                 int32_t* out_index_dev, uint8_t* out_low_conf_dev, void* stream);
+
+/*
  * Validation hook for the tensor-core path (K2): raw cosine scores of B queries against rows
  * [row_begin, row_end) as computed by the tcgen05 contraction (bf16 queries x bf16 rows, fp32 accumulate),
  * written to out_scores_dev[b * out_ld + (row - row_begin)].  workspace as for mmr_search(B, k = 10).

@@ -33,6 +33,7 @@ SYMBOLS = [
     ("mmr_search_exchange_workspace_bytes", _sz, [_p, _i32, _i32]),
     ("mmr_search_exchange", C.c_int, [_p, _p, _p, _i32, _i32, _p, _i32, _i32, C.c_uint32, _p, _p, _p, _sz, _p]),
     ("mmr_fuse", C.c_int, [_p, _p, _i32, _p, _p, _i32, _i32, _i32, _f64, _p, _p, _p, _p, _p, _p]),
+    ("mmr_fuse_f64", C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _f64, _p, _p, _p, _p]),
     ("mmr_debug_umma_scores", C.c_int, [_p, _p, _i32, _i64, _i64, _p, _i64, _p, _sz, _p]),
     ("mmr_launch_count", _i64, []),
     ("mmr_device_sm_count", C.c_int, [C.c_int, C.POINTER(C.c_int)]),

@@ -254,6 +254,92 @@ __device__ __forceinline__ void np_z_scores(const float* cos, int n, double* v, 
   }
 }
 
+// z-scores of n python-float scores v (float64) -> z; same arithmetic as np_z_scores without the cosine step
+__device__ __forceinline__ void np_z_scores_f64(const double* v, int n, double* z) {
+  float arr[FUSE_MAXK], sq[FUSE_MAXK];
+  for (int i = 0; i < n; ++i) arr[i] = __double2float_rn(v[i]);
+  const float fn = float(n);
+  const float mean = __fdiv_rn(np_pairwise_sum_f32(arr, n), fn);
+  for (int i = 0; i < n; ++i) {
+    const float x = __fsub_rn(arr[i], mean);
+    sq[i] = __fmul_rn(x, x);
+  }
+  const float sd = __fsqrt_rn(__fdiv_rn(np_pairwise_sum_f32(sq, n), fn));
+  if (sd == 0.f) {
+    for (int i = 0; i < n; ++i) z[i] = 0.0;
+  } else {
+    const double dm = double(mean), ds = double(sd);
+    for (int i = 0; i < n; ++i) z[i] = __ddiv_rn(__dsub_rn(v[i], dm), ds);
+  }
+}
+
+// stable descending order of key[0..n) -> idx (insertion sort: n <= 128, one thread per request)
+__device__ __forceinline__ void stable_desc_order(const double* key, int n, int* idx) {
+  for (int i = 0; i < n; ++i) {
+    int j = i;
+    while (j > 0 && key[idx[j - 1]] < key[i]) {
+      idx[j] = idx[j - 1];
+      --j;
+    }
+    idx[j] = i;
+  }
+}
+
+// K5 (complete form): _rerank_text's reordering + _fuse_results + _confidence_low for one request per thread, from the
+// float64 scores the reference sees (reference app/ml/retrieve.py:132-195, app/ml/generate.py:56-60).
+//   text_scores [B, kt] in scan order, text_count [B]; rerank [B, kt]: the cross-encoder logits, assigned -- exactly
+//   as `zip(top_candidates, scores)` does -- to the FIRST rr_count[b] text items (rr_count NULL / 0 = no rerank);
+//   img_scores [B, ki], img_count [B].  out_index: text item j (scan position) -> j, image item j -> kt + j, -1 = none.
+__global__ void fuse_full_kernel(const double* __restrict__ text_scores, const int32_t* __restrict__ text_count,
+                                 const double* __restrict__ rerank, const int32_t* __restrict__ rr_count,
+                                 const double* __restrict__ img_scores, const int32_t* __restrict__ img_count, int kt,
+                                 int ki, int B, int final_n, double tau, double* __restrict__ out_combined,
+                                 int32_t* __restrict__ out_index, uint8_t* __restrict__ out_low_conf) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int nt = text_count ? min(text_count[b], kt) : 0;
+  const int ni = img_count ? min(img_count[b], ki) : 0;
+  const int nr = (rr_count && rerank) ? min(rr_count[b], nt) : 0;
+  double key[FUSE_MAXK], v[FUSE_MAXK], z[FUSE_MAXK], rr[FUSE_MAXK], zr[FUSE_MAXK];
+  double comb[2 * FUSE_MAXK];
+  int order[FUSE_MAXK], src[2 * FUSE_MAXK], fin[2 * FUSE_MAXK];
+  // _rerank_text: sort by rerank_score where present, else score (stable, descending); untouched without logits
+  for (int j = 0; j < nt; ++j) {
+    key[j] = j < nr ? rerank[size_t(b) * kt + j] : text_scores[size_t(b) * kt + j];
+    order[j] = j;
+  }
+  if (nr > 0) stable_desc_order(key, nt, order);
+  // _fuse_results
+  int nrr = 0;
+  for (int j = 0; j < nt; ++j) {
+    v[j] = text_scores[size_t(b) * kt + order[j]];
+    if (order[j] < nr) rr[nrr++] = rerank[size_t(b) * kt + order[j]];
+  }
+  if (nt) np_z_scores_f64(v, nt, z);
+  if (nrr) np_z_scores_f64(rr, nrr, zr);
+  for (int j = 0; j < nt; ++j) {
+    // np.mean of [z_cos] or [z_cos, z_rerank]: pairwise sum starting at 0.0, then a true divide by the count
+    comb[j] = j < nrr ? __ddiv_rn(__dadd_rn(__dadd_rn(0.0, z[j]), zr[j]), 2.0) : __ddiv_rn(__dadd_rn(0.0, z[j]), 1.0);
+    src[j] = order[j];
+  }
+  if (ni) {
+    for (int j = 0; j < ni; ++j) v[j] = img_scores[size_t(b) * ki + j];
+    np_z_scores_f64(v, ni, z);
+    for (int j = 0; j < ni; ++j) {
+      comb[nt + j] = z[j];
+      src[nt + j] = kt + j;
+    }
+  }
+  const int n = nt + ni;
+  stable_desc_order(comb, n, fin);
+  for (int o = 0; o < final_n; ++o) {
+    const size_t oo = size_t(b) * final_n + o;
+    out_combined[oo] = o < n ? comb[fin[o]] : 0.0;
+    out_index[oo] = o < n ? src[fin[o]] : -1;
+  }
+  out_low_conf[b] = (n == 0 || final_n <= 0) ? 1 : (comb[fin[0]] < tau ? 1 : 0);
+}
+
 __global__ void fuse_kernel(const float* __restrict__ text_scores, const int64_t* __restrict__ text_rows, int kt,
                             const float* __restrict__ img_scores, const int64_t* __restrict__ img_rows, int ki, int B,
                             int final_n, double tau, double* __restrict__ out_combined,

@@ -749,3 +749,24 @@ extern "C" int mmr_fuse(const float* text_scores_dev, const int64_t* text_rows_d
   CUDA_TRY(cudaGetLastError());
   return MMR_OK;
 }
+
+extern "C" int mmr_fuse_f64(const double* text_scores_dev, const int32_t* text_count_dev, const double* text_rerank_dev,
+                            const int32_t* rerank_count_dev, const double* img_scores_dev, const int32_t* img_count_dev,
+                            int32_t kt, int32_t ki, int32_t B, int32_t final_n, double tau, double* out_combined_dev,
+                            int32_t* out_index_dev, uint8_t* out_low_conf_dev, void* stream) {
+  if (B <= 0) return fail(MMR_ERR_INVALID, "B must be >= 1");
+  if (kt < 0 || kt > FUSE_MAXK || ki < 0 || ki > FUSE_MAXK) return fail(MMR_ERR_INVALID, "kt, ki must be in [0, %d]", FUSE_MAXK);
+  if (final_n < 1) return fail(MMR_ERR_INVALID, "final_n must be >= 1");
+  if ((kt > 0 && (!text_scores_dev || !text_count_dev)) || (ki > 0 && (!img_scores_dev || !img_count_dev)))
+    return fail(MMR_ERR_INVALID, "NULL input buffer");
+  if (!out_combined_dev || !out_index_dev || !out_low_conf_dev) return fail(MMR_ERR_INVALID, "NULL output buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int threads = 32;
+  fuse_full_kernel<<<(B + threads - 1) / threads, threads, 0, st>>>(
+      kt > 0 ? text_scores_dev : nullptr, kt > 0 ? text_count_dev : nullptr, text_rerank_dev, rerank_count_dev,
+      ki > 0 ? img_scores_dev : nullptr, ki > 0 ? img_count_dev : nullptr, kt, ki, B, final_n, tau, out_combined_dev,
+      out_index_dev, out_low_conf_dev);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return MMR_OK;
+}

@@ -220,3 +220,26 @@ def fuse(text: Optional[Tuple[torch.Tensor, torch.Tensor]], image: Optional[Tupl
                                  b, int(final_n), float(tau), comb.data_ptr(), score.data_ptr(), rows.data_ptr(),
                                  mod.data_ptr(), low.data_ptr(), _stream_ptr(dev)))
     return {"combined": comb, "score": score, "rows": rows, "modality": mod, "low_conf": low}
+
+
+def fuse_f64(text_scores, text_count, img_scores, img_count, final_n: int, tau: float, rerank=None, rerank_count=None):
+    """K5, complete form (mmr_fuse_f64): float64 scores [B, kt] / [B, ki] + counts (+ optional cross-encoder logits for
+    the first rerank_count[b] text items) -> {"combined" [B, final_n] f64, "index" [B, final_n] i32, "low_conf" [B] u8}."""
+    ref = text_scores if text_scores is not None else img_scores
+    dev = ref.device
+    b = int(ref.shape[0])
+    kt = 0 if text_scores is None else int(text_scores.shape[1])
+    ki = 0 if img_scores is None else int(img_scores.shape[1])
+    comb = torch.empty((b, final_n), dtype=torch.float64, device=dev)
+    index = torch.empty((b, final_n), dtype=torch.int32, device=dev)
+    low = torch.empty((b,), dtype=torch.uint8, device=dev)
+
+    def p(t, dt):
+        return None if t is None else t.to(device=dev, dtype=dt).contiguous()
+
+    ts, tc, rr, rc = p(text_scores, torch.float64), p(text_count, torch.int32), p(rerank, torch.float64), p(rerank_count, torch.int32)
+    is_, ic = p(img_scores, torch.float64), p(img_count, torch.int32)
+    with torch.cuda.device(dev):
+        N.check(N.lib().mmr_fuse_f64(_ptr(ts), _ptr(tc), _ptr(rr), _ptr(rc), _ptr(is_), _ptr(ic), kt, ki, b, int(final_n),
+                                     float(tau), comb.data_ptr(), index.data_ptr(), low.data_ptr(), _stream_ptr(dev)))
+    return {"combined": comb, "index": index, "low_conf": low}

@@ -280,3 +280,61 @@ def test_retrieve_batch_device_equals_host_retrieve(mmr):
     assert [it["chunk_id"] for it in again[0][0]] == [h["chunk_id"] for h in retrieve.retrieve(*reqs[0])]
     assert victim not in [it["chunk_id"] for it in again[0][0]]
     cache.clear_all_caches()
+
+
+def _replay_on_device(mmr, text, image, final_n, tau, logits=None):
+    """One golden request through mmr_fuse_f64; returns ([(kind, position, combined)], low_conf)."""
+    kt, ki = len(text), len(image)
+    ts = torch.tensor([[it["score"] for it in text]], dtype=torch.float64, device="cuda") if kt else None
+    tc = torch.tensor([kt], dtype=torch.int32, device="cuda") if kt else None
+    is_ = torch.tensor([[it["score"] for it in image]], dtype=torch.float64, device="cuda") if ki else None
+    ic = torch.tensor([ki], dtype=torch.int32, device="cuda") if ki else None
+    rr = rc = None
+    if logits and kt:
+        padded = list(logits) + [0.0] * (kt - len(logits))
+        rr = torch.tensor([padded], dtype=torch.float64, device="cuda")
+        rc = torch.tensor([len(logits)], dtype=torch.int32, device="cuda")
+    if not kt and not ki:
+        return [], True
+    out = mmr.fuse_f64(ts, tc, is_, ic, final_n, tau, rerank=rr, rerank_count=rc)
+    comb, idx = out["combined"][0].cpu().tolist(), out["index"][0].cpu().tolist()
+    items = [(("t", i) if i < kt else ("i", i - kt)) + (c,) for c, i in zip(comb, idx) if i >= 0]
+    return items, bool(out["low_conf"][0].item())
+
+
+def test_fuse_kernel_reproduces_reference_outputs_on_golden_vectors(mmr):
+    """mmr_fuse_f64 against what the REFERENCE'S OWN _rerank_text / _fuse_results / _confidence_low returned when
+    oracle/make_golden.py executed them: same winners in the same order, bit-identical float64 combined scores."""
+    with open(os.path.join(HERE, "golden", "fusion_golden.json")) as fh:
+        golden = json.load(fh)
+    checked = 0
+    for case in golden["fuse"]:
+        text, image = case["text"], case["image"]
+        got, low = _replay_on_device(mmr, text, image, case["final_n"], 0.25)
+        want = case["expect"]
+        pos_t = {it["chunk_id"]: j for j, it in enumerate(text)}
+        pos_i = {it["chunk_id"]: j for j, it in enumerate(image)}
+        assert len(got) == len(want)
+        for (kind, pos, comb), w in zip(got, want):
+            assert (kind, pos) == (("t", pos_t[w["chunk_id"]]) if w["modality"] == "text" else ("i", pos_i[w["chunk_id"]]))
+            assert comb == w["combined_score"]
+        assert low is ofu.confidence_low(want, 0.25)
+        checked += 1
+    for case in golden["rerank_fuse"]:
+        text, image = case["text"], case["image"]
+        # the logits went to the first len(predict) of the first rerank_topk items (zip in _rerank_text)
+        got, low = _replay_on_device(mmr, text, image, case["final_n"], 0.25, logits=case["predict"])
+        want = case["expect"]
+        pos_t = {it["chunk_id"]: j for j, it in enumerate(text)}
+        pos_i = {it["chunk_id"]: j for j, it in enumerate(image)}
+        assert len(got) == len(want), case["rerank_topk"]
+        for (kind, pos, comb), w in zip(got, want):
+            assert (kind, pos) == (("t", pos_t[w["chunk_id"]]) if w["modality"] == "text" else ("i", pos_i[w["chunk_id"]]))
+            assert comb == w["combined_score"]
+        assert low is ofu.confidence_low(want, 0.25)
+        checked += 1
+    assert checked == len(golden["fuse"]) + len(golden["rerank_fuse"]) == 58
+    # the reference repository's own fixture (tests/test_retrieve.py:46-52 with the linspace cross encoder)
+    first = golden["rerank_fuse"][0]
+    got, _ = _replay_on_device(mmr, first["text"], first["image"], 4, 0.25, logits=first["predict"])
+    assert [(k, p) for k, p, _ in got] == [("i", 0), ("t", 0), ("t", 1)]
