@@ -40,8 +40,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Remote arrive with the default (.release.cta) semantics: the arriving warps publish nothing through ordinary memory
+// (tensor-memory reads are ordered by tcgen05.fence::before_thread_sync), and a cluster-scope release costs a full
+// memory barrier per arrive -- it was 31 % of all stall samples in the first version (profiles/r01_k2_summary.md).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_512_2sm(uint32_t dst_smem) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(512u) : "memory");
@@ -381,11 +384,10 @@ inline int umma_search(UmmaIndexState& st, Umma2IndexState& st2, const void* row
     cudaFuncSetAttribute(scan_umma2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_LIMIT);
     attr_set = true;
   }
-  // CTA pairs (cta_group::2) for the tensor-bound regime (at least two query tiles).  Measured on B200 (round 1,
-  // profiles/r01_k2_summary.md): parity-green but 5-10 % SLOWER than cta_group::1 here (B=1024: 9.18 vs 8.31 ms) --
-  // the kernel is clock/power-limited rather than shared-memory-limited -- so it is opt-in: MMR_UMMA_PAIR=1.
+  // CTA pairs (cta_group::2) for the tensor-bound regime (at least two query tiles): 5-9 % faster than cta_group::1
+  // there (B=1024: 8.30 vs 8.72 ms, profiles/r01_k2_summary.md).  MMR_UMMA_PAIR=0 falls back to single CTAs.
   const char* pair_env = getenv("MMR_UMMA_PAIR");
-  bool pair = ts && umma_qtiles(B) >= 2 && (pair_env && pair_env[0] == '1');
+  bool pair = ts && umma_qtiles(B) >= 2 && !(pair_env && pair_env[0] == '0');
   size_t smem2_bytes = 0;
   const int stages2 = umma2_plan_stages(k, &smem2_bytes);
   if (stages2 < 4) pair = false;
