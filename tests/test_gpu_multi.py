@@ -54,6 +54,25 @@ def _worker(rank, world, port, ret):
         for (mode, b, k), r in results.items():
             if mode != "nccl":
                 assert torch.equal(r, results[("nccl", b, k)])
+        # tenants: segments that straddle shard boundaries keep their id on every shard that holds a slice of them
+        sharded_mod = importlib.import_module(PKG + ".sharded")
+        seg = np.array([0, 1000, 1000, 140_000, 260_000, n], dtype=np.int64)
+        local_seg = pkg.ResidentIndex(full_dev[lo:hi].contiguous(), seg_offsets=sharded_mod.split_segments(seg, lo, hi), row_base=lo)
+        single_seg = pkg.ResidentIndex(full_dev, seg_offsets=seg)
+        os.environ["MMR_PDL"] = "0"
+        for mode in ("nccl", "fused"):
+            sh = pkg.ShardedIndex(local_seg, exchange=mode)
+            for tenants in ([2], [3, 3, 3, 3, 3], [0, 2, 3, 4, 1, -1]):
+                b = len(tenants)
+                qd = torch.from_numpy(util.queries(b, 512, seed=900 + b)).cuda()
+                s, r = sh.search(qd, 10, tenants)
+                torch.cuda.synchronize()
+                s1, r1 = single_seg.search(qd, 10, tenants)
+                assert torch.equal(r, r1) and torch.equal(s, s1), f"{mode} tenants {tenants} rank{rank}"
+                for j, t in enumerate(tenants):
+                    if t >= 0:
+                        ok = (r[j] < 0) | ((r[j] >= int(seg[t])) & (r[j] < int(seg[t + 1])))
+                        assert bool(ok.all())
         if rank == 0:
             ret["ok"] = True
     finally:
