@@ -25,3 +25,31 @@ def test_plain_c_client(tmp_path):
     run = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert run.returncode == 0, run.stdout + run.stderr
     assert "abi_smoke: ok" in run.stdout
+
+
+def test_integration_md_ctypes_stub_runs():
+    """The binding printed in INTEGRATION.md (examples/ctypes_stub.py is the same code) against the oracle."""
+    import importlib.util
+
+    import numpy as np
+    import torch
+
+    from oracle import flat_search as ofs
+    from tests import util
+
+    spec = importlib.util.spec_from_file_location("ctypes_stub", os.path.join(ROOT, "examples", "ctypes_stub.py"))
+    stub = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(stub)
+    rows = util.unit_rows(30_000, 512, seed=3)
+    dev_rows = torch.from_numpy(rows).cuda().to(torch.bfloat16)
+    seg = [0, 10_000, 30_000]
+    table = stub.ResidentTable(dev_rows, seg, [f"c{i}" for i in range(30_000)], ['{"i": %d}' % i for i in range(30_000)],
+                               {"alice": 0, "bob": 1})
+    q = util.queries(1, 512)[0]
+    hits = table.search("bob", q.tolist(), 12)
+    d, ids = ofs.flat_search(rows, q, 12, lo=10_000, hi=30_000)
+    assert len(hits) == 12 and hits[0]["chunk_id"] == f"c{ids[0]}"
+    assert abs(hits[0]["score"] - (1.0 - float(d[0]))) < util.TOL_BF16
+    assert hits[0]["meta"] == {"i": int(ids[0])}
+    assert table.search("nobody", q.tolist(), 12) == []
+    assert len(table.search("alice", q.tolist(), 0)) == 1
