@@ -338,3 +338,19 @@ def test_fuse_kernel_reproduces_reference_outputs_on_golden_vectors(mmr):
     first = golden["rerank_fuse"][0]
     got, _ = _replay_on_device(mmr, first["text"], first["image"], 4, 0.25, logits=first["predict"])
     assert [(k, p) for k, p, _ in got] == [("i", 0), ("t", 0), ("t", 1)]
+
+
+def test_store_fp32_storage_meets_the_1e5_tolerance(mmr):
+    """dtype="f32" keeps the reference's stored precision: scores within 1e-5 of the oracle store, same ids."""
+    users = ["a", "b"]
+    rows = _rows(4000, 512, 21, users, "i")
+    gpu, cpu = mmr.B200Store(dtype="f32"), ofs.OracleStore()
+    gpu.upsert_image_vectors([mmr.VectorRow(**r.__dict__) for r in rows])
+    cpu.upsert_image_vectors(rows)
+    rng = np.random.default_rng(22)
+    for u in users:
+        for _ in range(5):
+            q = rng.standard_normal(512).astype(np.float32)
+            got, want = gpu.search_image(u, q.tolist(), 12), cpu.search_image(u, q.tolist(), 12)
+            assert [g["chunk_id"] for g in got] == [w["chunk_id"] for w in want]
+            assert max(abs(g["score"] - w["score"]) for g, w in zip(got, want)) <= util.TOL_F32

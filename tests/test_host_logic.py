@@ -203,3 +203,40 @@ def test_batched_metadata_join_is_used_when_offered(monkeypatch):
     _wire(monkeypatch, DummyStore(text_rows, []), Meta(), False)
     got = retrieve.retrieve_text("u", "q")
     assert [g["chunk_id"] for g in got] == ["a", "b"] and calls == {"bulk": 1, "single": 0}
+
+
+def test_host_fusion_matches_oracle_on_random_requests():
+    """Property check: the product's host fusion (_rerank_text + _fuse_results + _confidence_low) against the
+    golden-pinned oracle on seeded random requests (ties, empty lists, partial rerank, every FINAL_N)."""
+    from oracle import fusion as ofu
+
+    rng = np.random.default_rng(99)
+    for trial in range(300):
+        nt, ni = int(rng.integers(0, 51)), int(rng.integers(0, 13))
+        quant = rng.choice([0, 2, 4])                       # coarse scores -> ties
+        def scores(n, lo, hi):
+            s = rng.uniform(lo, hi, size=n)
+            s = np.round(s, quant) if quant else s
+            return sorted((float(np.float32(x)) if trial % 2 else float(x) for x in s), reverse=True)
+        text = [{"chunk_id": f"t{j}", "modality": "text", "score": sc, "metadata": {}, "text": "" if rng.random() < 0.1 else f"x{j}"}
+                for j, sc in enumerate(scores(nt, -0.2, 0.95))]
+        image = [{"chunk_id": f"i{j}", "modality": "image", "score": sc, "metadata": {}, "text": None}
+                 for j, sc in enumerate(scores(ni, 0.0, 0.5))]
+        final_n, rerank_topk = int(rng.choice([1, 4, 10, 70])), int(rng.choice([0, 3, 8, 60]))
+        tau = float(rng.choice([0.0, 0.25, 0.9]))
+        logits = [float(x) for x in rng.normal(0, 3, size=64).astype(np.float32)]
+        use_rerank = bool(trial % 3)
+        cfg = settings_mod.RetrievalSettings(use_rerank=use_rerank, rerank_topk=rerank_topk, final_n=final_n, confidence_tau=tau)
+        retrieve.settings.retrieval = cfg
+        model = SimpleNamespace(predict=lambda pairs: logits[: len(pairs)])
+        old = retrieve._get_cross_encoder
+        retrieve._get_cross_encoder = lambda: model
+        try:
+            mine = retrieve._fuse_results(retrieve._rerank_text("q", copy.deepcopy(text)), copy.deepcopy(image))
+            low = retrieve._confidence_low(mine)
+        finally:
+            retrieve._get_cross_encoder = old
+        ref_r = ofu.rerank_text("q", copy.deepcopy(text), lambda pairs: logits[: len(pairs)], use_rerank, rerank_topk)
+        ref = ofu.fuse_results(ref_r, copy.deepcopy(image), final_n)
+        assert mine == ref, trial
+        assert low is ofu.confidence_low(ref, tau)
