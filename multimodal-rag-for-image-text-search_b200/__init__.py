@@ -11,8 +11,9 @@ from .index import ResidentIndex, fuse, fuse_f64, merge_topk
 from .sharded import ShardedIndex, shard_bounds
 from .store import B200Store, VectorRow, make_arrow_table
 from .settings import RetrievalSettings, load_retrieval_settings
+from .batcher import MicroBatcher
 
 __all__ = [
     "ResidentIndex", "B200Store", "VectorRow", "RetrievalSettings", "load_retrieval_settings", "NativeError",
-    "merge_topk", "fuse", "fuse_f64", "ShardedIndex", "shard_bounds", "make_arrow_table", "build_native",
+    "merge_topk", "fuse", "fuse_f64", "ShardedIndex", "shard_bounds", "make_arrow_table", "build_native", "MicroBatcher",
 ]

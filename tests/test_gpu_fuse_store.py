@@ -354,3 +354,52 @@ def test_store_fp32_storage_meets_the_1e5_tolerance(mmr):
             got, want = gpu.search_image(u, q.tolist(), 12), cpu.search_image(u, q.tolist(), 12)
             assert [g["chunk_id"] for g in got] == [w["chunk_id"] for w in want]
             assert max(abs(g["score"] - w["score"]) for g, w in zip(got, want)) <= util.TOL_F32
+
+
+def test_micro_batched_requests_equal_per_request_retrieve(mmr):
+    """48 request threads -> MicroBatcher -> retrieve_batch_device (batched scans + K5): every thread gets exactly what
+    the per-request host path returns, and the requests shared launches."""
+    import threading
+
+    retrieve = importlib.import_module(PKG + ".retrieve")
+    cache = importlib.import_module(PKG + ".cache")
+    settings_mod = importlib.import_module(PKG + ".settings")
+    cache.clear_all_caches()
+    n_t, n_i = 5000, 2000
+    temb, iemb = util.unit_rows(n_t, 384, 25), util.unit_rows(n_i, 512, 26)
+    users = [f"u{j}" for j in range(6)]
+    store = mmr.B200Store()
+    store.load_arrow("text_collection", mmr.make_arrow_table([f"t{i}" for i in range(n_t)], [users[i % 6] for i in range(n_t)],
+                                                             ["d"] * n_t, ["text"] * n_t, temb, ["{}"] * n_t))
+    store.load_arrow("image_collection", mmr.make_arrow_table([f"i{i}" for i in range(n_i)], [users[i % 6] for i in range(n_i)],
+                                                              ["d"] * n_i, ["image"] * n_i, iemb, ["{}"] * n_i))
+    chunks = {f"t{i}": SimpleNamespace(id=f"t{i}", document_id="d", modality="text", text=f"text {i}", meta={},
+                                       page_no=i, start_ts=None, end_ts=None, file_path=None) for i in range(n_t)}
+    chunks.update({f"i{i}": SimpleNamespace(id=f"i{i}", document_id="d", modality="image", text=None, meta={},
+                                            page_no=None, start_ts=None, end_ts=None, file_path=f"/f/{i}.jpg") for i in range(n_i)})
+    nq = 48
+    qtext = {f"query {j}": util.queries(1, 384, seed=300 + j)[0] for j in range(nq)}
+    qimg = {f"query {j}": util.queries(1, 512, seed=400 + j)[0] for j in range(nq)}
+    retrieve.configure(store=store, metadata=SimpleNamespace(get_chunk=chunks.get),
+                       text_encoder=lambda texts: qtext[texts[0]][None, :], image_query_encoder=lambda q: qimg[q],
+                       retrieval_settings=settings_mod.RetrievalSettings(use_rerank=False))
+    store.search_text(users[0], qtext["query 0"].tolist(), 1)          # build the resident copies before the threads start
+    store.search_image(users[0], qimg["query 0"].tolist(), 1)
+    got = {}
+    with mmr.MicroBatcher(retrieve.retrieve_batch_device, max_batch=32, max_wait_ms=50.0) as mb:
+        def client(j):
+            got[j] = mb.retrieve(users[j % 6], f"query {j}", timeout=60)
+        threads = [threading.Thread(target=client, args=(j,)) for j in range(nq)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(60)
+        assert sum(mb.batches) == nq and len(mb.batches) < nq
+    for j in range(nq):
+        cache.clear_all_caches()
+        host = retrieve.retrieve(users[j % 6], f"query {j}")
+        items, low = got[j]
+        assert [it["chunk_id"] for it in items] == [h["chunk_id"] for h in host], j
+        assert [it["combined_score"] for it in items] == [h["combined_score"] for h in host]
+        assert low is retrieve._confidence_low(host)
+    cache.clear_all_caches()
