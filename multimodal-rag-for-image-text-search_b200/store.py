@@ -298,9 +298,68 @@ class B200Store:
         if not torch.cuda.is_available():
             raise N.NativeError("no CUDA device: B200Store has no CPU fallback")
         self._device = torch.device(device)
+        self._db_path = db_path
         self._text_table = _Collection("text_collection", self._device, dtype)
         self._image_table = _Collection("image_collection", self._device, dtype)
         self._versions = VersionFile(os.path.join(db_path, "index_versions.json") if db_path else None)
+        if db_path:
+            # durable state next to index_versions.json: one Arrow IPC file per collection with the reference schema
+            # (what LanceDB keeps as .lance fragments); a restarted process reloads them into HBM
+            for coll in (self._text_table, self._image_table):
+                path = os.path.join(db_path, coll.name + ".arrow")
+                if os.path.exists(path):
+                    self._load_ipc(coll, path)
+
+    @staticmethod
+    def _load_ipc(coll: "_Collection", path: str) -> None:
+        import pyarrow as pa
+        import pyarrow.ipc as ipc
+
+        with pa.memory_map(path, "r") as src:
+            table = ipc.open_file(src).read_all()
+        if table.num_rows:
+            B200Store._load_table(coll, table)
+
+    @staticmethod
+    def _load_table(coll: "_Collection", table) -> List[str]:
+        emb = table.column("embedding").combine_chunks()
+        offsets = emb.offsets.to_numpy()
+        widths = np.diff(offsets)
+        if widths.size and (widths != widths[0]).any():
+            raise ValueError(f"{coll.name}: variable-length embeddings are not supported by the resident scan")
+        flat = emb.values.to_numpy(zero_copy_only=False)[offsets[0]:offsets[-1]]
+        mat = np.ascontiguousarray(flat, dtype=np.float32).reshape(table.num_rows, int(widths[0]))
+        cols = {c: table.column(c).to_pylist() for c in ("chunk_id", "user_id", "document_id", "modality", "meta")}
+        coll.load_columns(cols["chunk_id"], cols["user_id"], cols["document_id"], cols["modality"], cols["meta"], mat)
+        return sorted(set(map(str, cols["user_id"])))
+
+    def load_arrow_ipc(self, collection: str, path: str) -> None:
+        """Bulk-load an Arrow IPC file written with the reference schema (see make_arrow_table / persist)."""
+        import pyarrow as pa
+        import pyarrow.ipc as ipc
+
+        with pa.memory_map(path, "r") as src:
+            self.load_arrow(collection, ipc.open_file(src).read_all())
+
+    def persist(self) -> None:
+        """Write both collections (live rows, host order) as Arrow IPC files under db_path."""
+        import pyarrow as pa
+        import pyarrow.ipc as ipc
+
+        if not self._db_path:
+            raise ValueError("B200Store was created without a db_path")
+        os.makedirs(self._db_path, exist_ok=True)
+        for coll in (self._text_table, self._image_table):
+            alive = np.nonzero(np.asarray(coll._alive, dtype=bool))[0]
+            if alive.size == 0:
+                continue
+            table = make_arrow_table([coll.chunk_id[i] for i in alive], [coll.user_id[i] for i in alive],
+                                     [coll.document_id[i] for i in alive], [coll.modality[i] for i in alive],
+                                     coll._host_rows(alive), [coll.meta[i] for i in alive])
+            tmp = os.path.join(self._db_path, coll.name + ".arrow.tmp")
+            with pa.OSFile(tmp, "wb") as sink, ipc.new_file(sink, table.schema) as writer:
+                writer.write_table(table)
+            os.replace(tmp, os.path.join(self._db_path, coll.name + ".arrow"))
 
     # writes (lancedb_store.py:87-101) + version bump (index_build.py:102,148)
     def upsert_text_vectors(self, rows: Iterable[VectorRow]) -> None:
@@ -318,19 +377,9 @@ class B200Store:
         """Bulk-load a pyarrow Table with the reference schema (chunk_id, user_id, document_id, modality,
         embedding: list<float32>, meta) -- what `lancedb.Table.to_arrow()` yields."""
         coll = {"text_collection": self._text_table, "image_collection": self._image_table}[collection]
-        n = table.num_rows
-        if n == 0:
+        if table.num_rows == 0:
             return
-        emb = table.column("embedding").combine_chunks()
-        offsets = emb.offsets.to_numpy()
-        widths = np.diff(offsets)
-        if widths.size and (widths != widths[0]).any():
-            raise ValueError(f"{collection}: variable-length embeddings are not supported by the resident scan")
-        flat = emb.values.to_numpy(zero_copy_only=False)[offsets[0]:offsets[-1]]
-        mat = np.ascontiguousarray(flat, dtype=np.float32).reshape(n, int(widths[0]))
-        cols = {c: table.column(c).to_pylist() for c in ("chunk_id", "user_id", "document_id", "modality", "meta")}
-        coll.load_columns(cols["chunk_id"], cols["user_id"], cols["document_id"], cols["modality"], cols["meta"], mat)
-        for user in sorted(set(map(str, cols["user_id"]))):
+        for user in self._load_table(coll, table):
             self._versions.bump(user)
 
     # reads (lancedb_store.py:103-123)

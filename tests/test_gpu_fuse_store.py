@@ -403,3 +403,29 @@ def test_micro_batched_requests_equal_per_request_retrieve(mmr):
         assert [it["combined_score"] for it in items] == [h["combined_score"] for h in host]
         assert low is retrieve._confidence_low(host)
     cache.clear_all_caches()
+
+
+def test_persist_and_restart(mmr, tmp_path):
+    """Durable state = Arrow IPC files with the reference schema + index_versions.json; a new process (new store on the
+    same path) reloads them into HBM and answers identically."""
+    db = str(tmp_path / "lance_db")
+    rows_t, rows_i = _rows(1500, 384, 31, ["a", "b"], "t"), _rows(700, 512, 32, ["a", "b"], "i")
+    s1 = mmr.B200Store(db)
+    s1.upsert_text_vectors([mmr.VectorRow(**r.__dict__) for r in rows_t])
+    s1.upsert_image_vectors([mmr.VectorRow(**r.__dict__) for r in rows_i])
+    s1.upsert_text_vectors([mmr.VectorRow(**rows_t[3].__dict__)])        # an overwrite: only the live copy is persisted
+    s1.persist()
+    assert sorted(os.listdir(db)) == ["image_collection.arrow", "index_versions.json", "text_collection.arrow"]
+    s2 = mmr.B200Store(db)
+    assert len(s2._text_table) == 1500 and len(s2._image_table) == 700
+    assert s2.get_index_version("a") == s1.get_index_version("a") >= 2
+    rng = np.random.default_rng(33)
+    for u in ("a", "b"):
+        qt, qi = rng.standard_normal(384).astype(np.float32), rng.standard_normal(512).astype(np.float32)
+        assert s2.search_text(u, qt.tolist(), 20) == s1.search_text(u, qt.tolist(), 20)
+        assert s2.search_image(u, qi.tolist(), 12) == s1.search_image(u, qi.tolist(), 12)
+    import pyarrow as pa, pyarrow.ipc as ipc
+    with pa.memory_map(os.path.join(db, "text_collection.arrow"), "r") as src:
+        schema = ipc.open_file(src).schema
+    assert [f.name for f in schema] == ["chunk_id", "user_id", "document_id", "modality", "embedding", "meta"]
+    assert str(schema.field("embedding").type) == "list<item: float>"
