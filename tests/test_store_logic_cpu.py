@@ -1,0 +1,159 @@
+"""Host logic of B200Store (collections, tenant ranges, tombstones, compaction, versions, persistence) on CPU.
+
+The scan itself only exists on the GPU, so ResidentIndex is replaced here by a numpy stand-in with the same interface
+(test infrastructure, like the reference's DummyStore); everything above it -- the code that decides WHICH rows a tenant
+owns after any sequence of upserts -- is the product code under test."""
+import copy
+import importlib
+import json
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import flat_search as ofs
+
+PKG = "multimodal-rag-for-image-text-search_b200"
+store_mod = importlib.import_module(PKG + ".store")
+
+
+class FakeIndex:
+    """numpy stand-in for ResidentIndex: exact fp32 scan, NaN rows never returned, order (score desc, row asc)."""
+
+    def __init__(self, rows, seg_offsets=None, row_base=0):
+        self.rows, self.n_rows, self.dim = rows, int(rows.shape[0]), int(rows.shape[1])
+        self.seg_offsets = None if seg_offsets is None else np.asarray(seg_offsets, np.int64)
+        self.device = rows.device
+
+    @classmethod
+    def from_f32(cls, rows_f32, seg_offsets=None, dtype="bf16", device="cpu", normalize=False, row_base=0):
+        return cls(torch.from_numpy(np.ascontiguousarray(rows_f32, dtype=np.float32)).clone(), seg_offsets, row_base)
+
+    def update(self, rows, n_rows=None, seg_offsets=None):
+        self.rows, self.n_rows = rows, int(rows.shape[0] if n_rows is None else n_rows)
+        self.seg_offsets = None if seg_offsets is None else np.asarray(seg_offsets, np.int64)
+
+    def close(self):
+        pass
+
+    def _scan(self, q, k, ranges):
+        mat = self.rows[: self.n_rows].numpy()
+        qn = np.asarray(ofs.normalize(q), np.float32)
+        idx = np.concatenate([np.arange(lo, hi) for lo, hi in ranges] + [np.zeros(0, np.int64)]).astype(np.int64)
+        s = mat[idx] @ qn
+        keep = ~np.isnan(s)
+        idx, s = idx[keep], s[keep]
+        order = np.lexsort((idx, -s.astype(np.float64)))[:k]
+        out_s, out_r = np.full(k, -np.inf, np.float32), np.full(k, -1, np.int64)
+        out_s[: len(order)], out_r[: len(order)] = s[order], idx[order]
+        return out_s, out_r
+
+    def search_host(self, q, k, segments=None):
+        q = np.atleast_2d(q)
+        res = [self._scan(q[b], k, [(int(self.seg_offsets[segments[b]]), int(self.seg_offsets[segments[b] + 1]))])
+               for b in range(q.shape[0])]
+        return np.stack([r[0] for r in res]), np.stack([r[1] for r in res])
+
+    def search_ranges(self, q, k, ranges):
+        q = q.numpy()
+        res = [self._scan(q[b], k, ranges[b]) for b in range(q.shape[0])]
+        return torch.from_numpy(np.stack([r[0] for r in res])), torch.from_numpy(np.stack([r[1] for r in res]))
+
+
+@pytest.fixture
+def cpu_store(monkeypatch, tmp_path):
+    monkeypatch.setattr(store_mod, "ResidentIndex", FakeIndex)
+
+    def make(db_path=None):
+        st = store_mod.B200Store.__new__(store_mod.B200Store)       # skip the CUDA checks of __init__
+        st._device = torch.device("cpu")
+        st._db_path = db_path
+        st._text_table = store_mod._Collection("text_collection", st._device, "f32")
+        st._image_table = store_mod._Collection("image_collection", st._device, "f32")
+        st._versions = importlib.import_module(PKG + ".versions").VersionFile(
+            os.path.join(db_path, "index_versions.json") if db_path else None)
+        if db_path:
+            for coll in (st._text_table, st._image_table):
+                path = os.path.join(db_path, coll.name + ".arrow")
+                if os.path.exists(path):
+                    store_mod.B200Store._load_ipc(coll, path)
+        return st
+
+    return make
+
+
+def _mk(rng, ids, user_of, dim=384):
+    return [SimpleNamespace(chunk_id=f"t{i}", user_id=user_of(i), document_id="d", modality="text",
+                            embedding=rng.standard_normal(dim).astype(np.float32).tolist(), meta={"i": int(i)}) for i in ids]
+
+
+def _same(got, want, tol=1e-5):
+    assert [g["chunk_id"] for g in got] == [w["chunk_id"] for w in want]
+    assert all(abs(g["score"] - w["score"]) <= tol and g["meta"] == w["meta"] for g, w in zip(got, want))
+
+
+def test_upserts_overwrites_and_compaction_track_the_oracle(cpu_store):
+    rng = np.random.default_rng(1)
+    users = ["a", "b", "c"]
+    gpu, cpu = cpu_store(), ofs.OracleStore()
+    first = _mk(rng, range(900), lambda i: users[i % 3])
+    gpu.upsert_text_vectors([store_mod.VectorRow(**r.__dict__) for r in first])
+    cpu.upsert_text_vectors(first)
+    next_id = 900
+    for step in range(14):
+        batch = _mk(rng, range(next_id, next_id + 12), lambda i: users[(i * 5) % 3]) + \
+                _mk(rng, rng.choice(next_id, size=9, replace=False), lambda i: users[i % 3])
+        if step == 4:
+            batch += [copy.deepcopy(batch[0])]                       # the same chunk twice in one batch: last one wins
+            batch[-1].embedding = rng.standard_normal(384).astype(np.float32).tolist()
+        next_id += 12
+        gpu.upsert_text_vectors([store_mod.VectorRow(**r.__dict__) for r in batch])
+        if step == 4:
+            cpu.upsert_text_vectors(batch[:-1]); cpu.upsert_text_vectors(batch[-1:])
+        else:
+            cpu.upsert_text_vectors(batch)
+        for u in users + ["nobody"]:
+            q = rng.standard_normal(384).astype(np.float32)
+            _same(gpu.search_text(u, q.tolist(), 10), cpu.search_text(u, q.tolist(), 10))
+        qs = rng.standard_normal((4, 384)).astype(np.float32)
+        for u, q, b in zip(["a", "c", "nobody", "b"], qs, gpu.search_text_batch(["a", "c", "nobody", "b"], qs, 5)):
+            _same(b, cpu.search_text(u, q.tolist(), 5))
+    coll = gpu._text_table
+    assert coll.appends >= 6 and 2 <= coll.rebuilds <= 6          # deltas most of the time, compaction when ranges pile up
+    assert all(len(r) < coll.MAX_RANGES for r in coll._ranges.values())
+    assert len(coll) == len({c for c in cpu._text_table.chunk_id})
+    assert gpu.get_index_version("a") == 15 and gpu.get_index_version("nobody") == 0
+    assert gpu.search_text("a", rng.standard_normal(384).tolist(), 0).__len__() == 1     # max(top_k, 1)
+    with pytest.raises(store_mod.N.NativeError):
+        gpu.search_text("a", rng.standard_normal(384).tolist(), 65)
+
+
+def test_empty_store_and_mixed_dims(cpu_store):
+    st = cpu_store()
+    assert st.search_text("u", [0.0] * 384, 5) == [] and st.search_image_batch(["u"], np.zeros((1, 512)), 5) == [[]]
+    st.upsert_text_vectors([])
+    st.upsert_image_vectors([store_mod.VectorRow("i1", "u", "d", "image", [1.0] * 512, {})])
+    with pytest.raises(ValueError):
+        st.upsert_image_vectors([store_mod.VectorRow("i2", "u", "d", "image", [1.0] * 384, {})])
+    hit = st.search_image("u", [2.0] * 512, 3)
+    assert [h["chunk_id"] for h in hit] == ["i1"] and abs(hit[0]["score"] - 1.0) < 1e-6 and hit[0]["meta"] == {}
+
+
+def test_persist_and_reload(cpu_store, tmp_path):
+    rng = np.random.default_rng(2)
+    db = str(tmp_path / "db")
+    s1 = cpu_store(db)
+    rows = _mk(rng, range(300), lambda i: "a" if i % 2 else "o'brien")
+    s1.upsert_text_vectors([store_mod.VectorRow(**r.__dict__) for r in rows])
+    s1.upsert_text_vectors([store_mod.VectorRow(**rows[7].__dict__)])
+    s1.persist()
+    s2 = cpu_store(db)
+    assert len(s2._text_table) == 300 and s2.get_index_version("o'brien") == s1.get_index_version("o'brien")
+    q = rng.standard_normal(384).astype(np.float32).tolist()
+    assert s2.search_text("o'brien", q, 12) == s1.search_text("o'brien", q, 12)
+    table = store_mod.make_arrow_table(["x"], ["u"], ["d"], ["text"], np.ones((1, 384), np.float32), [None])
+    assert table.schema.names == ["chunk_id", "user_id", "document_id", "modality", "embedding", "meta"]
+    s2.load_arrow("text_collection", table)
+    assert s2.search_text("u", [1.0] * 384, 1)[0]["chunk_id"] == "x"
