@@ -1,4 +1,4 @@
-// K1 -- HBM-streaming exact scan for small query groups (1..4 queries sharing one row range).
+// K1 -- HBM-streaming exact scan for small query groups (1..4 queries sharing one row range, 8 on fp32 rows).
 //
 // Replaces the Lance flat KNN behind LanceDBStore.search_text / search_image
 // (reference app/storage/lancedb_store.py:103-123): cos(q, x_n) for every row of the tenant's row

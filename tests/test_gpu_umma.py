@@ -1,4 +1,4 @@
-"""K2: the tcgen05/TMEM contraction with the fused top-k epilogue (query batches > 4 sharing one row range)."""
+"""K2: the tcgen05/TMEM contraction with the fused top-k epilogue (query batches of 3 or more sharing one row range)."""
 import importlib
 
 import numpy as np
