@@ -6,7 +6,7 @@ import os
 from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmmr_b200.so")
+LIB_PATH = os.environ.get("MMR_LIB_PATH") or os.path.join(HERE, "libmmr_b200.so")  # override: experiments only
 
 MMR_OK = 0
 MMR_BF16, MMR_F32, MMR_F16 = 0, 1, 2

@@ -292,7 +292,7 @@ static int launch_stream(const mmr_index* ix, const StreamParams& p, int nq_pad,
   return fail(MMR_ERR_UNSUPPORTED, "no stream kernel for dtype %d dim %d", ix->dtype, ix->dim);
 }
 
-static int rows_per_stage(int dtype) { return dtype == MMR_F32 ? 4 : 8; }
+static int rows_per_stage(int) { return MMR_K1_ROWS; }
 
 // ------------------------------------------------------------------------------------------------ planning
 // Workspace layout (bytes):

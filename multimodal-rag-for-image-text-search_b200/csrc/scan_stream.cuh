@@ -25,9 +25,20 @@
 
 namespace mmr {
 
-constexpr int K1_NW = 8;           // consumer warps per CTA
+// Ring geometry, tuned on B200 (profiles/r01_k1_summary.md, "bytes in flight"): 8 warps x 2 stages x 4 rows.
+// Fewer bytes in flight per SM stream FASTER here: 64 KB/SM reached 7.4-7.5 TB/s where the first version's 192 KB/SM
+// (3 stages x 8 rows) reached 6.8-6.9 TB/s on the same box; 2-row stages lose again (per-stage overheads).
+#ifndef MMR_K1_NW
+#define MMR_K1_NW 8
+#endif
+#ifndef MMR_K1_STAGES
+#define MMR_K1_STAGES 2
+#endif
+#ifndef MMR_K1_ROWS
+#define MMR_K1_ROWS 4
+#endif
+constexpr int K1_NW = MMR_K1_NW;   // consumer warps per CTA
 constexpr int K1_THREADS = K1_NW * 32;
-constexpr int K1_SMEM_BUDGET = 200 * 1024;
 constexpr int MMR_MAX_PEERS = 16;
 
 struct ScanItem {  // varlen mode: one contiguous row range of one query (rows are index-local ordinals)
@@ -119,11 +130,10 @@ template <typename E, int D, int NQ, int KPL>
 struct StreamCfg {
   static constexpr int EB = ElemTraits<E>::BYTES;
   static constexpr int ROW_BYTES = D * EB;
-  static constexpr int R = (EB == 2) ? 8 : 4;                        // rows per stage
+  static constexpr int R = MMR_K1_ROWS;                              // rows per stage
   static constexpr int V = R * NQ;                                   // dot products per stage per warp
   static constexpr int STAGE_BYTES = R * ROW_BYTES;
-  static constexpr int S_RAW = K1_SMEM_BUDGET / (K1_NW * STAGE_BYTES);
-  static constexpr int S = S_RAW > 4 ? 4 : S_RAW;                    // stages per warp
+  static constexpr int S = MMR_K1_STAGES;                            // stages per warp
   static constexpr int VECB = (ROW_BYTES % 512 == 0) ? 16 : 8;       // bytes per lane per vector load
   static constexpr int NV = ROW_BYTES / (32 * VECB);                 // vector loads per lane per row
   static constexpr int RPV = VECB / 4;                               // 32-bit registers per vector
