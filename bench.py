@@ -26,6 +26,21 @@ import sys
 import threading
 import time
 
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# The CPU arm must use every host core it is allowed to: torchrun exports OMP_NUM_THREADS=1 to its children, which
+# would silently make the BLAS scan single-threaded.  The BLAS pool is sized when numpy is first imported, so the
+# variables are overridden HERE, before that import (and re-checked with threadpoolctl in run_reference).
+if "reference" in sys.argv:
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(host_cores())
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -63,6 +78,14 @@ def measured_peaks():
             d = json.load(fh)
         return float(d["hbm_gbs"]), float(d.get("bf16_tflops", 1590.0)), "measured"
     return 6650.0, 1590.0, "fallback"
+
+
+def load_traffic():
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return {}
 
 
 # --------------------------------------------------------------------------------------------- synthetic data
@@ -159,74 +182,125 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
-def cpu_flat_search_qps(rows_f32: np.ndarray, queries: np.ndarray, k: int, total_rows: int, budget_s: float = 12.0):
-    """Oracle flat search (numpy/OpenBLAS fp32) on a bounded sample; qps extrapolated linearly to total_rows."""
-    from oracle import flat_search as ofs
-    b = queries.shape[0]
-    reps, t_used = 0, 0.0
-    ofs.flat_search_batch(rows_f32[:50_000], queries, k)  # warm BLAS threads
-    while t_used < budget_s and reps < 50:
-        t0 = time.perf_counter()
-        if b == 1:
-            ofs.flat_search(rows_f32, queries[0], k)
-        else:
-            ofs.flat_search_batch(rows_f32, queries, k)
-        t_used += time.perf_counter() - t0
-        reps += 1
-    per_pass = t_used / reps
-    scale = total_rows / rows_f32.shape[0]
-    return b / (per_pass * scale), per_pass, reps
-
-
-def host_cores():
+def host_mem_available_gb() -> float:
     try:
-        return len(os.sched_getaffinity(0))
+        with open("/proc/meminfo") as fh:
+            for line in fh:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) / 1e6
     except Exception:
-        return os.cpu_count() or 1
+        pass
+    return 0.0
 
 
-def sample_rows_host(n: int, dim: int) -> np.ndarray:
-    """The first n rows of the synthetic table, regenerated on the host's GPU-independent path when no GPU is
-    around (numpy) -- used only by the reference arm when CUDA is unavailable."""
-    rng = np.random.default_rng(SEED)
-    x = rng.standard_normal((n, dim), dtype=np.float32)
-    x /= np.linalg.norm(x, axis=1, keepdims=True)
-    return x
+def host_table(n: int, dim: int, threads: int) -> np.ndarray:
+    """The CPU arm's fp32 table: n unit-norm rows of the same distribution as the GPU arm's synthetic table
+    (normalised N(0,1)^dim; the reference stores fp32, lancedb_store.py:33-44), generated block by block from
+    (SEED, block id) in `threads` threads.  Only the distribution matters for timing a flat scan."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    out = np.empty((n, dim), dtype=np.float32)
+
+    def fill(b):
+        s, e = b * BLOCK_ROWS, min((b + 1) * BLOCK_ROWS, n)
+        rng = np.random.default_rng([SEED, b])
+        blk = out[s:e]
+        rng.standard_normal(out=blk, dtype=np.float32)
+        blk /= np.sqrt(np.einsum("ij,ij->i", blk, blk))[:, None]
+
+    with ThreadPoolExecutor(max(1, threads)) as pool:
+        list(pool.map(fill, range((n + BLOCK_ROWS - 1) // BLOCK_ROWS)))
+    return out
+
+
+def blas_threads() -> int:
+    try:
+        from threadpoolctl import threadpool_info
+        return max([int(i.get("num_threads", 1)) for i in threadpool_info()] or [1])
+    except Exception:
+        return -1
+
+
+class CpuReference:
+    """The reference's CPU flat search (restated in oracle/, kind "port": the real one runs inside lancedb/lance, not
+    installable here) on this box's host cores.  One object = one resident fp32 table; `search` is one pass."""
+
+    def __init__(self, rows: int, dim: int):
+        self.cores = host_cores()
+        # the whole table when host memory allows it (10M x 512 fp32 = 20.5 GB), else a bounded sample scaled up
+        need_gb = rows * dim * 4 / 1e9
+        self.n = rows if host_mem_available_gb() > need_gb + 8.0 else min(rows, 1_000_000)
+        self.scale = rows / self.n
+        t0 = time.perf_counter()
+        self.table = host_table(self.n, dim, self.cores)
+        self.gen_s = time.perf_counter() - t0
+        self.mode = None
+
+    def _pass(self, q, k, mode):
+        from oracle import flat_search as ofs
+        if mode == "blas":      # one multi-threaded sgemv/sgemm over the table + partition
+            return ofs.flat_search_batch(self.table, q, k) if q.shape[0] > 1 else ofs.flat_search(self.table, q[0], k)
+        return ofs.flat_search_threads(self.table, q, k, self.cores)   # row slices on a thread pool
+
+    def calibrate(self, q, k):
+        """Pick the faster of the two threadings once (after one untimed pass each)."""
+        best = None
+        for mode in ("blas", "slices"):
+            self._pass(q, k, mode)
+            t0 = time.perf_counter()
+            self._pass(q, k, mode)
+            dt = time.perf_counter() - t0
+            if best is None or dt < best[0]:
+                best = (dt, mode)
+        self.mode = best[1]
+        return best
+
+    def search(self, q, k):
+        return self._pass(q, k, self.mode)
+
+    def describe(self) -> dict:
+        whole = self.n * self.scale == self.n
+        return {"cores": self.cores, "kind": "port", "blas_threads": blas_threads(), "threading": self.mode,
+                "sample": (f"all {self.n} rows per pass" if self.scale == 1.0 else
+                           f"first {self.n} rows per pass, time x{self.scale:g} (host memory too small for the fp32 table)"),
+                "note": "numpy/OpenBLAS fp32 restatement of the flat search (oracle/), not LanceDB; fp32 rows as the "
+                        "reference stores them"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = min(args.cpu_sample_rows, args.rows)
-    rows = sample_rows_host(n, args.dim)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=host_cores())
+    except Exception:
+        pass
+    cpu = CpuReference(args.rows, args.dim)
     qs = gen_queries((args.warmup + args.steps) * args.batch, args.dim).reshape(-1, args.batch, args.dim)
-    from oracle import flat_search as ofs
-    n_warm = 5  # untimed passes: BLAS thread pool spin-up and page faults would otherwise land in the first steps
+    cpu.calibrate(qs[0], args.k)
+    n_warm = max(1, min(args.warmup, 3))
     for i in range(n_warm):
-        ofs.flat_search_batch(rows, qs[i % len(qs)], args.k)
+        cpu.search(qs[i % len(qs)], args.k)
     steps = 0
     t0 = time.perf_counter()
-    while steps < max(1, args.steps) and (steps < 3 or time.perf_counter() - t0 < 90.0):
-        q = qs[args.warmup + steps]
-        if args.batch == 1:
-            ofs.flat_search(rows, q[0], args.k)
-        else:
-            ofs.flat_search_batch(rows, q, args.k)
+    while steps < max(1, args.steps) and (steps < 3 or time.perf_counter() - t0 < 120.0):
+        cpu.search(qs[args.warmup + steps], args.k)
         steps += 1
-    dt = (time.perf_counter() - t0) / steps
-    scale = args.rows / n
-    qps = args.batch / (dt * scale)
+    dt = (time.perf_counter() - t0) / steps * cpu.scale
+    qps = args.batch / dt
+    desc = cpu.describe()
     line = {
         "impl": "reference", "metric": METRIC, "value": qps,
         "unit": "queries/s", "n_gpus": args.gpus, "steps": steps, "warmup": n_warm,
-        "ms_per_step": dt * scale * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.rows}x{args.dim} {args.dtype} unit-norm rows, top-{args.k}, query batch {args.batch}",
                    "note": "CPU arm: the reference's scan lives in lancedb/lance (not installable here); the restated numpy "
-                           "flat search scans the fp32 rows the reference stores"},
-        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": host_cores(), "kind": "port",
-                         "sample": f"first {n} of {args.rows} rows per step, time x{scale:g}"},
+                           "flat search scans the fp32 rows the reference stores",
+                   "host_threads": desc["cores"], "blas_threads": desc["blas_threads"], "threading": desc["threading"],
+                   "table_gen_s": round(cpu.gen_s, 2)},
+        "cpu_baseline": dict(desc, value=qps, unit="queries/s"),
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -271,6 +345,41 @@ def run_b200(args):
         if world > 1:
             return sharded.search(q_dev[i], k)   # local scan -> one packed all-gather -> K4 merge in place
         return ix.search(q_dev[i], k, out=(out_s, out_r))
+
+    # ---- parity inside the bench run: k exact copies of warm-up query 0 are planted on both sides of every shard
+    # boundary (and at the table's first / last row); the search must return exactly those rows, in row order, with
+    # equal scores, and -- for N > 1 -- the fused peer-memory exchange must equal the NCCL all-gather path bit for bit.
+    cand = [0, args.rows - 1]
+    for r in range(1, world):
+        cand += [bounds[r] - 1, bounds[r]]
+    for extra in range(1, 4 * k):
+        cand += [args.rows // 2 + 7919 * extra]
+    planted = []
+    for c in cand:
+        if 0 <= c < args.rows and c not in planted:
+            planted.append(c)
+        if len(planted) == k:
+            break
+    planted.sort()
+    mine = [c for c in planted if lo <= c < hi]
+    if mine:
+        ix.rows[torch.tensor([c - lo for c in mine], device=device)] = q_dev[0, 0].to(ix.rows.dtype)
+    torch.cuda.synchronize(device)
+    pq = q_dev[0, :1].contiguous()
+    if world > 1:
+        fused_s, fused_r = [t.clone() for t in sharded.search(pq, k)]
+        nccl = pkg.ShardedIndex(ix, exchange="nccl")
+        nccl_s, nccl_r = nccl.search(pq, k)
+        torch.cuda.synchronize(device)
+        assert torch.equal(fused_r, nccl_r) and torch.equal(fused_s, nccl_s), \
+            f"rank {rank}: {sharded.exchange} exchange and NCCL all-gather + merge disagree"
+        par_s, par_r = fused_s, fused_r
+        del nccl
+    else:
+        par_s, par_r = [t.clone() for t in ix.search(pq, k)]
+    assert par_r[0].cpu().tolist() == planted, f"rank {rank}: planted rows {planted} came back as {par_r[0].cpu().tolist()}"
+    assert bool((par_s[0] == par_s[0, 0]).all()) and float(par_s[0, 0]) > 0.99, "planted copies must tie at cosine ~1"
+    parity_checked = True
 
     def barrier():
         if world > 1:
@@ -333,8 +442,12 @@ def run_b200(args):
                           2: "scan_umma_kernel (K2, tcgen05/TMEM contraction + fused top-k)",
                           3: "scan_stream_kernel varlen"}.get(kern)
     roofline["kernel_ms"] = kernel_ms
-    if kern == 1 and B == 1 and D == 512 and args.dtype == "bf16" and hi - lo == 10_000_000:
-        roofline["traffic"] = 10_240_285_000  # dram__bytes_read+write per launch, ncu --set full, profiles/r01_k1_summary.md
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
+    # capture of this exact workload (profiles/roofline_traffic.json names the .csv each figure was read from)
+    traffic = load_traffic().get(f"k{kern}_{args.dtype}_{hi - lo}x{D}_b{B}_k{k}")
+    if traffic:
+        roofline["traffic"] = traffic["dram_bytes_per_launch"]
+        roofline["traffic_source"] = traffic["source"]
 
     # end to end through the host-buffer C-ABI call (pinned staging, H2D, scan, D2H, sync) -- rank-local shard;
     # for N > 1 the gather + merge of the tiny [G,B,k] lists is included via the device path above.
@@ -394,14 +507,16 @@ def run_b200(args):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n = min(args.cpu_sample_rows, hi - lo)
-        sample = ix.rows[:n].to(torch.float32).cpu().numpy() if args.dtype != "f32" else ix.rows[:n].cpu().numpy()
-        # the CPU path scans the fp32 table the reference stores; values = the same synthetic rows
-        v, per_pass, reps = cpu_flat_search_qps(sample, q_host[W], k, args.rows)
-        cpu_baseline = {"value": v, "unit": "queries/s", "cores": host_cores(), "kind": "port",
-                        "sample": f"first {n} of {args.rows} rows, {reps} passes of {per_pass*1e3:.1f} ms, time x{args.rows / n:g}",
-                        "note": "numpy/OpenBLAS fp32 restatement of the flat search (oracle/), not LanceDB"}
-        # sanity: the GPU result of the last step agrees with the oracle on the sample's rows
+        # the same CPU path as `--impl reference` (that arm is THE baseline; this is its in-run copy on a ~15 s budget)
+        cpu = CpuReference(args.rows, D)
+        cpu.calibrate(q_host[0], k)
+        reps, t0 = 0, time.perf_counter()
+        while reps < 3 or (time.perf_counter() - t0 < 12.0 and reps < 50):
+            cpu.search(q_host[W + reps % K], k)
+            reps += 1
+        per_pass = (time.perf_counter() - t0) / reps * cpu.scale
+        cpu_baseline = dict(cpu.describe(), value=B / per_pass, unit="queries/s", passes=reps, ms_per_pass=per_pass * 1e3)
+        del cpu
     if rank == 0:
         line = {
             "metric": METRIC,
@@ -417,6 +532,9 @@ def run_b200(args):
                                  + ("on" if os.environ.get("MMR_PDL") == "1" else "off")},
             "hbm_GBs_aggregate": args.rows * D * esize / (ms_step * 1e-3) / 1e9,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "parity_checked": parity_checked,
+            "parity": {"planted_rows": planted, "what": "k copies of a query across every shard boundary returned exactly, "
+                       "in row order" + ("; fused exchange == NCCL all-gather + merge, bit for bit" if world > 1 else "")},
             "clocks": clocks.summary(), "sweep": sweep or None,
         }
         print(json.dumps(line), flush=True)

@@ -196,6 +196,39 @@ def flat_search_batch(
     return best_d, best_i
 
 
+def flat_search_threads(
+    rows: np.ndarray,
+    queries: np.ndarray,
+    k: int,
+    threads: int,
+    lo: int = 0,
+    hi: Optional[int] = None,
+) -> Tuple[np.ndarray, np.ndarray]:
+    """``flat_search_batch`` with the row range cut into ``threads`` contiguous slices scanned concurrently
+    (numpy releases the GIL inside the sgemm and the partition), then one stable merge in slice order.
+
+    Same results as ``flat_search_batch`` (same tie rule: slices are concatenated in ordinal order).  This is the
+    "all host cores" form of the CPU baseline in bench.py: Lance's flat scan is multi-threaded too.
+    """
+    from concurrent.futures import ThreadPoolExecutor
+
+    hi = rows.shape[0] if hi is None else hi
+    k = max(int(k), 1)
+    queries = np.atleast_2d(np.asarray(queries, dtype=np.float32))
+    n = max(hi - lo, 0)
+    threads = max(1, min(int(threads), (n + 65535) // 65536 or 1))
+    if threads == 1:
+        return flat_search_batch(rows, queries, k, lo, hi)
+    cuts = [lo + (n * t) // threads for t in range(threads + 1)]
+    with ThreadPoolExecutor(threads) as pool:
+        parts = list(pool.map(lambda t: flat_search_batch(rows, queries, k, cuts[t], cuts[t + 1]), range(threads)))
+    alld = np.concatenate([p[0] for p in parts], axis=1)
+    alli = np.concatenate([p[1] for p in parts], axis=1)
+    kk = min(k, n)
+    o = np.argsort(alld, axis=1, kind="stable")[:, :kk]
+    return np.take_along_axis(alld, o, axis=1), np.take_along_axis(alli, o, axis=1)
+
+
 # --------------------------------------------------------------------------- result shaping
 def format_results(rows: List[Dict[str, Any]]) -> List[Dict[str, Any]]:
     """lancedb_store.py:125-139 -- similarity = 1.0 - float(_distance); stable sort by score desc."""
