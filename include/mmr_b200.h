@@ -80,6 +80,16 @@ int mmr_convert_rows_f32(const float* src_dev, void* dst_dev, int dtype, int64_t
 int mmr_load_rows_f32_host(int device, const float* src_host, void* dst_dev, int dtype, int64_t n_rows, int dim,
                            int normalize, void* stream);
 
+/* Same, with a row map: source row i is written to resident row dst_row_host[i]; negative entries are skipped.  This is
+ * how the store uploads a host block in insertion order straight into its tenant-sorted place (the tenant grouping that
+ * replaces the `user_id == '...'` filter, lancedb_store.py:107,118) without gathering 20 GB on the host.  NULL = identity.
+ * dst_dev is the BASE of the resident matrix in this form. */
+int mmr_load_rows_f32_host_scatter(int device, const float* src_host, void* dst_dev, int dtype, int64_t n_rows, int dim,
+                                   int normalize, const int64_t* dst_row_host, void* stream);
+/* Host-only helper of the columnar store: 64-bit hashes of n strings held Arrow-style (byte buffer + n+1 int32 offsets),
+ * used to find the rows an upsert replaces (delete-by-chunk_id, lancedb_store.py:91-92). */
+int mmr_hash_strings(const uint8_t* data, const int32_t* offsets, int64_t n, uint64_t* out);
+
 /*
  * The scan: LanceDBStore.search_text / search_image (lancedb_store.py:103-123) for a batch of B queries.
  *   queries_dev     [B, dim] float32, any norm (re-normalised on device as :104 / :115 do).

@@ -23,6 +23,8 @@ SYMBOLS = [
     ("mmr_index_update", C.c_int, [_p, _i64, _p, _p, _i32]),
     ("mmr_convert_rows_f32", C.c_int, [_p, _p, C.c_int, _i64, C.c_int, C.c_int, _p]),
     ("mmr_load_rows_f32_host", C.c_int, [C.c_int, _p, _p, C.c_int, _i64, C.c_int, C.c_int, _p]),
+    ("mmr_load_rows_f32_host_scatter", C.c_int, [C.c_int, _p, _p, C.c_int, _i64, C.c_int, C.c_int, _p, _p]),
+    ("mmr_hash_strings", C.c_int, [_p, _p, _i64, _p]),
     ("mmr_search_workspace_bytes", _sz, [_p, _i32, _i32]),
     ("mmr_search", C.c_int, [_p, _p, _p, _i32, _i32, _p, _p, _p, _sz, _p]),
     ("mmr_search_ranges", C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _p, _p, _sz, _p]),

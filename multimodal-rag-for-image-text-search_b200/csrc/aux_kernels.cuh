@@ -21,14 +21,18 @@ __device__ __forceinline__ __half cast_elem<__half>(float x) { return __float2ha
 template <>
 __device__ __forceinline__ float cast_elem<float>(float x) { return x; }
 
+// dst_row != nullptr: source row i lands in resident row dst_row[i] (the tenant-sorted position the store computed);
+// a negative entry skips the row (deleted / superseded rows of a host block are streamed past, never gathered on the host).
 template <typename E>
 __global__ void convert_rows_kernel(const float* __restrict__ src, E* __restrict__ dst, int64_t n_rows, int dim,
-                                    int normalize) {
+                                    int normalize, const int64_t* __restrict__ dst_row = nullptr) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = int64_t(gridDim.x) * (blockDim.x >> 5);
   for (int64_t row = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_rows; row += warps) {
+    const int64_t drow = dst_row ? dst_row[row] : row;
+    if (drow < 0) continue;
     const float* s = src + row * dim;
-    E* d = dst + row * dim;
+    E* d = dst + drow * dim;
     float inv = 1.f;
     bool scale = false;
     if (normalize) {

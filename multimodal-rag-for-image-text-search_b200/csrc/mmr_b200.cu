@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "aux_kernels.cuh"
@@ -165,73 +166,139 @@ extern "C" int mmr_index_destroy(mmr_index* ix) {
 
 // ------------------------------------------------------------------------------------------------ loader
 template <typename E>
-static int launch_convert(const float* src, void* dst, int64_t n, int dim, int normalize, cudaStream_t st) {
+static int launch_convert(const float* src, void* dst, int64_t n, int dim, int normalize, cudaStream_t st,
+                          const int64_t* dst_row = nullptr) {
   if (n == 0) return MMR_OK;
   const int threads = 256;
   const int64_t blocks = std::min<int64_t>((n + 7) / 8, 148 * 16);
-  convert_rows_kernel<E><<<(unsigned)blocks, threads, 0, st>>>(src, reinterpret_cast<E*>(dst), n, dim, normalize);
+  convert_rows_kernel<E><<<(unsigned)blocks, threads, 0, st>>>(src, reinterpret_cast<E*>(dst), n, dim, normalize, dst_row);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return MMR_OK;
+}
+
+static int convert_dispatch(const float* src_dev, void* dst_dev, int dtype, int64_t n_rows, int dim, int normalize,
+                            cudaStream_t st, const int64_t* dst_row_dev) {
+  switch (dtype) {
+    case MMR_BF16: return launch_convert<__nv_bfloat16>(src_dev, dst_dev, n_rows, dim, normalize, st, dst_row_dev);
+    case MMR_F16: return launch_convert<__half>(src_dev, dst_dev, n_rows, dim, normalize, st, dst_row_dev);
+    case MMR_F32: return launch_convert<float>(src_dev, dst_dev, n_rows, dim, normalize, st, dst_row_dev);
+  }
+  return fail(MMR_ERR_INVALID, "unknown dtype %d", dtype);
 }
 
 extern "C" int mmr_convert_rows_f32(const float* src_dev, void* dst_dev, int dtype, int64_t n_rows, int dim,
                                     int normalize, void* stream) {
   if (n_rows < 0 || dim <= 0) return fail(MMR_ERR_INVALID, "bad shape");
   if (n_rows > 0 && (!src_dev || !dst_dev)) return fail(MMR_ERR_INVALID, "NULL buffer");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  switch (dtype) {
-    case MMR_BF16: return launch_convert<__nv_bfloat16>(src_dev, dst_dev, n_rows, dim, normalize, st);
-    case MMR_F16: return launch_convert<__half>(src_dev, dst_dev, n_rows, dim, normalize, st);
-    case MMR_F32: return launch_convert<float>(src_dev, dst_dev, n_rows, dim, normalize, st);
-  }
-  return fail(MMR_ERR_INVALID, "unknown dtype %d", dtype);
+  return convert_dispatch(src_dev, dst_dev, dtype, n_rows, dim, normalize, static_cast<cudaStream_t>(stream), nullptr);
 }
 
-extern "C" int mmr_load_rows_f32_host(int device, const float* src_host, void* dst_dev, int dtype, int64_t n_rows,
-                                      int dim, int normalize, void* stream) {
+// Pageable host memory -> pinned staging with a few threads (one memcpy thread tops out near 10 GB/s, well under the
+// PCIe gen5 link), double-buffered against the H2D copy + convert kernel of the previous chunk.
+static void parallel_memcpy(void* dst, const void* src, size_t bytes, int threads) {
+  if (threads <= 1 || bytes < (size_t(4) << 20)) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  std::vector<std::thread> pool;
+  const size_t per = (bytes / threads + 4095) / 4096 * 4096;
+  for (int t = 0; t < threads; ++t) {
+    const size_t o = size_t(t) * per;
+    if (o >= bytes) break;
+    const size_t len = std::min(per, bytes - o);
+    pool.emplace_back([=]() { memcpy(static_cast<uint8_t*>(dst) + o, static_cast<const uint8_t*>(src) + o, len); });
+  }
+  for (auto& th : pool) th.join();
+}
+
+extern "C" int mmr_load_rows_f32_host_scatter(int device, const float* src_host, void* dst_dev, int dtype, int64_t n_rows,
+                                              int dim, int normalize, const int64_t* dst_row_host, void* stream) {
   if (n_rows < 0 || dim <= 0) return fail(MMR_ERR_INVALID, "bad shape");
   if (n_rows == 0) return MMR_OK;
   if (!src_host || !dst_dev) return fail(MMR_ERR_INVALID, "NULL buffer");
+  if (dtype != MMR_BF16 && dtype != MMR_F32 && dtype != MMR_F16) return fail(MMR_ERR_INVALID, "unknown dtype %d", dtype);
   CUDA_TRY(cudaSetDevice(device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t chunk_rows = std::max<int64_t>(1, (int64_t(64) << 20) / (int64_t(dim) * 4));  // 64 MiB chunks
   const size_t chunk_bytes = size_t(chunk_rows) * dim * 4;
-  float* h[2] = {nullptr, nullptr};
-  float* d[2] = {nullptr, nullptr};
-  cudaEvent_t done[2];
+  const size_t map_bytes = dst_row_host ? size_t(chunk_rows) * 8 : 0;
+  uint8_t* h[2] = {nullptr, nullptr};
+  uint8_t* d[2] = {nullptr, nullptr};
+  cudaEvent_t done[2] = {nullptr, nullptr};
   int rc = MMR_OK;
   auto cleanup = [&]() {
     for (int i = 0; i < 2; ++i) {
       if (h[i]) cudaFreeHost(h[i]);
       if (d[i]) cudaFree(d[i]);
+      if (done[i]) cudaEventDestroy(done[i]);
     }
   };
   for (int i = 0; i < 2; ++i) {
-    if (cudaMallocHost(&h[i], chunk_bytes) != cudaSuccess || cudaMalloc(&d[i], chunk_bytes) != cudaSuccess) {
+    if (cudaMallocHost(&h[i], chunk_bytes + map_bytes) != cudaSuccess ||
+        cudaMalloc(&d[i], chunk_bytes + map_bytes) != cudaSuccess ||
+        cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess) {
       cleanup();
-      return fail(MMR_ERR_CUDA, "staging allocation of %zu bytes failed", chunk_bytes);
+      return fail(MMR_ERR_CUDA, "staging allocation of %zu bytes failed", chunk_bytes + map_bytes);
     }
-    cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
   }
-  const int eb = elem_bytes(dtype);
+  const int threads = int(std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2)));
   int slot = 0;
   for (int64_t r0 = 0; r0 < n_rows && rc == MMR_OK; r0 += chunk_rows, slot ^= 1) {
     const int64_t nr = std::min(chunk_rows, n_rows - r0);
+    const size_t bytes = size_t(nr) * dim * 4;
     cudaEventSynchronize(done[slot]);  // staging slot free again
-    memcpy(h[slot], src_host + r0 * dim, size_t(nr) * dim * 4);
-    if (cudaMemcpyAsync(d[slot], h[slot], size_t(nr) * dim * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+    parallel_memcpy(h[slot], src_host + r0 * dim, bytes, threads);
+    if (dst_row_host) memcpy(h[slot] + chunk_bytes, dst_row_host + r0, size_t(nr) * 8);
+    // one copy when the row map rides along (it sits right behind the chunk in both staging buffers)
+    const size_t copy_bytes = dst_row_host ? chunk_bytes + size_t(nr) * 8 : bytes;
+    if (cudaMemcpyAsync(d[slot], h[slot], copy_bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) {
       rc = fail(MMR_ERR_CUDA, "H2D copy failed");
       break;
     }
-    rc = mmr_convert_rows_f32(d[slot], static_cast<uint8_t*>(dst_dev) + size_t(r0) * dim * eb, dtype, nr, dim,
-                              normalize, st);
+    const int64_t* map_dev = dst_row_host ? reinterpret_cast<const int64_t*>(d[slot] + chunk_bytes) : nullptr;
+    const int eb = elem_bytes(dtype);
+    void* dst = dst_row_host ? dst_dev : static_cast<void*>(static_cast<uint8_t*>(dst_dev) + size_t(r0) * dim * eb);
+    rc = convert_dispatch(reinterpret_cast<const float*>(d[slot]), dst, dtype, nr, dim, normalize, st, map_dev);
     cudaEventRecord(done[slot], st);
   }
   cudaStreamSynchronize(st);
-  for (int i = 0; i < 2; ++i) cudaEventDestroy(done[i]);
   cleanup();
   return rc;
+}
+
+extern "C" int mmr_load_rows_f32_host(int device, const float* src_host, void* dst_dev, int dtype, int64_t n_rows,
+                                      int dim, int normalize, void* stream) {
+  return mmr_load_rows_f32_host_scatter(device, src_host, dst_dev, dtype, n_rows, dim, normalize, nullptr, stream);
+}
+
+// Host-side helper of the columnar store: 64-bit hashes of n strings held Arrow-style (one byte buffer + n+1 int32
+// offsets).  The store keeps (hash, row) sorted to find the rows an upsert replaces (delete-by-chunk_id,
+// lancedb_store.py:91-92) without a Python dict over millions of ids.
+extern "C" int mmr_hash_strings(const uint8_t* data, const int32_t* offsets, int64_t n, uint64_t* out) {
+  if (n < 0 || (n > 0 && (!offsets || !out))) return fail(MMR_ERR_INVALID, "bad arguments");
+  for (int64_t i = 0; i < n; ++i) {
+    const uint8_t* p = data + offsets[i];
+    const int32_t len = offsets[i + 1] - offsets[i];
+    uint64_t h = 0xcbf29ce484222325ull ^ (uint64_t(uint32_t(len)) * 0x9E3779B97F4A7C15ull);
+    int32_t j = 0;
+    for (; j + 8 <= len; j += 8) {
+      uint64_t w;
+      memcpy(&w, p + j, 8);
+      h = (h ^ w) * 0x100000001b3ull;
+      h ^= h >> 29;
+    }
+    uint64_t tail = 0;
+    if (j < len) memcpy(&tail, p + j, size_t(len - j));
+    h = (h ^ tail) * 0x100000001b3ull;
+    h ^= h >> 32;  // final avalanche (murmur3 fmix64)
+    h *= 0xff51afd7ed558ccdull;
+    h ^= h >> 33;
+    h *= 0xc4ceb9fe1a85ec53ull;
+    h ^= h >> 33;
+    out[i] = h;
+  }
+  return MMR_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ K1 launch
