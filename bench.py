@@ -65,6 +65,8 @@ def parse():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f16", "f32"])
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-store", action="store_true", help="N=1: build the table on the device instead of loading it "
+                    "through B200Store.load_arrow (e2e is then the bare host-buffer C call)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "nccl"],
                     help="N>1: fused = peer-memory stores from the scan kernel + wait/merge kernel; nccl = all-gather + merge")
     ap.add_argument("--sweep", default="8,128,1024", help="extra batch sizes reported under 'sweep' (N=1 only)")
@@ -122,6 +124,22 @@ def build_shard(pkg, lo: int, hi: int, dim: int, dtype: str, device):
         torch.cuda.synchronize(device)
         del blk, src
     return pkg.ResidentIndex(rows, row_base=lo)
+
+
+def planted_rows(n_rows: int, bounds, world: int, k: int):
+    """k row ordinals for the in-run parity check: first / last row, both sides of every shard boundary, a few more."""
+    cand = [0, n_rows - 1]
+    for r in range(1, world):
+        cand += [bounds[r] - 1, bounds[r]]
+    for extra in range(1, 4 * k):
+        cand += [n_rows // 2 + 7919 * extra]
+    planted = []
+    for c in cand:
+        if 0 <= c < n_rows and c not in planted:
+            planted.append(c)
+        if len(planted) == k:
+            break
+    return sorted(planted)
 
 
 # --------------------------------------------------------------------------------------------- clocks
@@ -327,15 +345,46 @@ def run_b200(args):
     # All queries of the timed loop are staged in HBM before it starts, so consecutive searches may be pipelined with
     # programmatic dependent launch (opt-in contract of the library, see csrc/mmr_b200.cu).
     if os.environ.get("MMR_PDL") is None:
-        os.environ["MMR_PDL"] = "1"
+        pkg._native.set_option("MMR_PDL", "1")
     B, k, D, K, W = args.batch, args.k, args.dim, args.steps, args.warmup
     # row-range shard of the one global table
     bounds = pkg.shard_bounds(args.rows, world)
     lo, hi = bounds[rank], bounds[rank + 1]
-    ix = build_shard(pkg, lo, hi, D, args.dtype, device)
     esize = 4 if args.dtype == "f32" else 2
-
     q_host = gen_queries((K + W) * B, D).reshape(K + W, B, D)
+    planted = planted_rows(args.rows, bounds, world, k)
+
+    # N = 1: the table goes the way a deployment loads it -- fp32 rows in the reference's Arrow schema ->
+    # B200Store.load_arrow (columnar host copy, scatter loader fp32 -> resident bf16) -- and every number below is taken
+    # on that store's resident index; the CPU arm scans the same host table.  N > 1 (one process per GPU): every rank
+    # generates its own row range on its GPU (the host could not hold N copies of the fp32 table).
+    store, cpu, load_info = None, None, None
+    use_store = world == 1 and not args.no_cpu_baseline and not args.no_store
+    if use_store:
+        cpu = CpuReference(args.rows, D)
+        use_store = cpu.scale == 1.0            # the whole table fits host memory
+    if use_store:
+        import pyarrow as pa
+        unit_q0 = q_host[0, 0] / np.linalg.norm(q_host[0, 0])
+        cpu.table[planted] = unit_q0              # the parity rows are part of the table itself (host AND device copy)
+        n = args.rows
+        t0 = time.perf_counter()
+        one = lambda v: pa.array([v], pa.string()).take(pa.array(np.zeros(n, np.int32)))
+        table = pkg.make_arrow_table(pa.array(np.arange(n)).cast(pa.string()), one("bench"), one("doc"), one("image"),
+                                     cpu.table, one("{}"))
+        t1 = time.perf_counter()
+        store = pkg.B200Store(device=device, dtype=args.dtype)
+        store.load_arrow("image_collection", table)
+        ix = store._image_table.resident()
+        torch.cuda.synchronize(device)
+        t2 = time.perf_counter()
+        load_info = {"api": "B200Store.load_arrow (reference 6-column schema, embedding column used zero-copy) + first resident()",
+                     "arrow_table_s": round(t1 - t0, 2), "load_s": round(t2 - t1, 2),
+                     "loader_GBs_fp32_source": store._image_table.last_load_gbs,
+                     "rows": n, "host_bytes": n * D * 4}
+        ix.set_query_precision("auto")            # the device-timed loops below measure the kernel families by batch size
+    else:
+        ix = build_shard(pkg, lo, hi, D, args.dtype, device)
     q_dev = torch.from_numpy(q_host).to(device)
     out_s = torch.empty((B, k), dtype=torch.float32, device=device)
     out_r = torch.empty((B, k), dtype=torch.int64, device=device)
@@ -349,21 +398,10 @@ def run_b200(args):
     # ---- parity inside the bench run: k exact copies of warm-up query 0 are planted on both sides of every shard
     # boundary (and at the table's first / last row); the search must return exactly those rows, in row order, with
     # equal scores, and -- for N > 1 -- the fused peer-memory exchange must equal the NCCL all-gather path bit for bit.
-    cand = [0, args.rows - 1]
-    for r in range(1, world):
-        cand += [bounds[r] - 1, bounds[r]]
-    for extra in range(1, 4 * k):
-        cand += [args.rows // 2 + 7919 * extra]
-    planted = []
-    for c in cand:
-        if 0 <= c < args.rows and c not in planted:
-            planted.append(c)
-        if len(planted) == k:
-            break
-    planted.sort()
-    mine = [c for c in planted if lo <= c < hi]
-    if mine:
-        ix.rows[torch.tensor([c - lo for c in mine], device=device)] = q_dev[0, 0].to(ix.rows.dtype)
+    if not use_store:
+        mine = [c for c in planted if lo <= c < hi]
+        if mine:
+            ix.rows[torch.tensor([c - lo for c in mine], device=device)] = q_dev[0, 0].to(ix.rows.dtype)
     torch.cuda.synchronize(device)
     pq = q_dev[0, :1].contiguous()
     if world > 1:
@@ -449,10 +487,42 @@ def run_b200(args):
         roofline["traffic"] = traffic["dram_bytes_per_launch"]
         roofline["traffic_source"] = traffic["source"]
 
-    # end to end through the host-buffer C-ABI call (pinned staging, H2D, scan, D2H, sync) -- rank-local shard;
-    # for N > 1 the gather + merge of the tiny [G,B,k] lists is included via the device path above.
+    # ---- end to end: the call a user of the drop-in makes, host buffers in, host results out, every step
     e2e = None
-    if world == 1:
+    if world == 1 and store is not None:
+        # LanceDBStore's own signature: search_image(user_id, query_vec: list of floats, top_k) -> list of dicts
+        ix.set_query_precision("f32")                        # the store's serving policy
+        qlists = [[q.tolist() for q in q_host[i]] for i in range(W + K)]
+        users = ["bench"] * B
+
+        def request(i):
+            if B == 1:
+                return [store.search_image("bench", qlists[i][0], k)]
+            return store.search_image_batch(users, q_host[i], k)
+
+        for i in range(min(W, 5)):
+            request(i)
+        t0 = time.perf_counter()
+        for i in range(W, W + K):
+            hits = request(i)
+        dt = (time.perf_counter() - t0) / K
+        e2e = {"value": B / dt, "unit": "queries/s", "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * k * 12,
+               "ms_per_step": dt * 1e3,
+               "api": "B200Store.search_image(user_id, list_of_floats, top_k) -> list of {chunk_id, score, meta} dicts, on the "
+                      f"{args.rows}-row collection loaded with load_arrow" if B == 1 else "B200Store.search_image_batch",
+               "transfers": "B <= 2: the query rides in the kernel parameters and the result lands in a mapped pinned mailbox "
+                            "(no cudaMemcpy); bytes counted are what crosses PCIe"}
+        got_rows = [int(h["chunk_id"]) for h in hits[0]]
+        if B <= 2:   # (larger batches: the store scores in fp32, the device loop above used the 16-bit tensor-core queries)
+            assert got_rows == last_rows[0].tolist(), "store path and device path disagree on the last step"
+        # the bare C call under it (what the store adds on top is Python: list -> ndarray, dict building, json.loads)
+        t0 = time.perf_counter()
+        for i in range(W, W + K):
+            hs, hr = ix.search_host(q_host[i], k)
+        e2e["c_abi_ms_per_step"] = (time.perf_counter() - t0) / K * 1e3
+        assert B > 2 or (hr == last_rows).all(), "host-buffer path and device path disagree"
+        ix.set_query_precision("auto")
+    elif world == 1:
         for i in range(min(W, 5)):
             ix.search_host(q_host[i], k)
         t0 = time.perf_counter()
@@ -463,25 +533,21 @@ def run_b200(args):
                "ms_per_step": dt * 1e3, "api": "mmr_search_host (the call B200Store.search_text/search_image make)"}
         assert (hr == last_rows).all(), "host-buffer path and device path disagree"
     else:
-        # host buffers in, device search + all-gather + merge, host result out, per step
-        pin_q = torch.from_numpy(q_host).pin_memory()
-        qd = torch.empty((B, D), dtype=torch.float32, device=device)
-        hs = torch.empty((B, k), dtype=torch.float32).pin_memory()
-        hr = torch.empty((B, k), dtype=torch.int64).pin_memory()
-        stream = torch.cuda.current_stream(device)
+        # one process per GPU: host query in, fused exchange, merged host result out (mmr_search_exchange_host)
+        barrier()
+        for i in range(min(W, 5)):
+            sharded.search_host(q_host[i], k)
         barrier()
         t0 = time.perf_counter()
         for i in range(W, W + K):
-            qd.copy_(pin_q[i], non_blocking=True)          # H2D from pinned memory
-            ms_, mr_ = sharded.search(qd, k)
-            hs.copy_(ms_, non_blocking=True)               # D2H into pinned memory, one sync for both
-            hr.copy_(mr_, non_blocking=True)
-            stream.synchronize()
+            hs, hr = sharded.search_host(q_host[i], k)
         dt = torch.tensor([(time.perf_counter() - t0) / K], device=device)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        assert (hr == last_rows).all(), "host-buffer exchange path and device path disagree"
         e2e = {"value": B / float(dt.item()), "unit": "queries/s", "h2d_bytes_per_step": B * D * 4,
                "d2h_bytes_per_step": B * k * 12, "ms_per_step": float(dt.item()) * 1e3,
-               "api": "ShardedIndex.search (scan + packed all-gather + merge) with pinned host query in / host result out"}
+               "api": "ShardedIndex.search_host (mmr_search_exchange_host: query in the scan kernel's parameters, fused "
+                      "peer-memory exchange, merged result + flag in a mapped pinned mailbox)"}
 
     # optional sweep over other batch sizes (device-resident timing only)
     sweep = []
@@ -507,15 +573,35 @@ def run_b200(args):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        # the same CPU path as `--impl reference` (that arm is THE baseline; this is its in-run copy on a ~15 s budget)
-        cpu = CpuReference(args.rows, D)
+        # the same CPU path as `--impl reference` (that arm is THE baseline; this is its in-run copy on a ~12 s budget),
+        # on the very table the GPU searched
+        if cpu is None:
+            cpu = CpuReference(args.rows, D)
         cpu.calibrate(q_host[0], k)
         reps, t0 = 0, time.perf_counter()
         while reps < 3 or (time.perf_counter() - t0 < 12.0 and reps < 50):
-            cpu.search(q_host[W + reps % K], k)
+            cd, ci = cpu.search(q_host[W + reps % K], k)
             reps += 1
         per_pass = (time.perf_counter() - t0) / reps * cpu.scale
         cpu_baseline = dict(cpu.describe(), value=B / per_pass, unit="queries/s", passes=reps, ms_per_pass=per_pass * 1e3)
+        if store is not None:
+            # oracle parity at full size, inside the run: the CPU flat search over the same 10M fp32 rows vs the GPU result
+            i = W + (reps - 1) % K
+            gs, gr = [t.cpu().numpy() for t in ix.search(q_dev[i], k)]
+            cd, ci = np.atleast_2d(cd), np.atleast_2d(ci)
+            tol = 1e-5 if args.dtype == "f32" else 1e-3
+            worst = 0.0
+            for b in range(B):
+                want = {int(r): 1.0 - float(d) for d, r in zip(cd[b], ci[b])}
+                kth = min(want.values())
+                for sc, r in zip(gs[b], gr[b]):
+                    assert int(r) in want or sc <= kth + tol, f"GPU hit {int(r)} ({sc}) is not in the oracle top-{k}"
+                    if int(r) in want:
+                        worst = max(worst, abs(want[int(r)] - float(sc)))
+                missing = [r for r, sc in want.items() if r not in set(gr[b].tolist()) and sc > kth + tol]
+                assert not missing, f"oracle hits {missing} missing from the GPU result"
+            assert worst <= tol, f"score error {worst} > {tol}"
+            cpu_baseline["oracle_parity_at_full_size"] = {"checked": True, "max_abs_score_err": worst, "tolerance": tol}
         del cpu
     if rank == 0:
         line = {
@@ -529,9 +615,9 @@ def run_b200(args):
                        "l2": "index (>= 1.28 GB per GPU) is larger than L2 (126 MB); no flush needed",
                        "rows_per_gpu": hi - lo,
                        "launch": "back-to-back searches on one stream, programmatic dependent launch "
-                                 + ("on" if os.environ.get("MMR_PDL") == "1" else "off")},
+                                 + ("on" if pkg._native.get_option("MMR_PDL") == 1 else "off")},
             "hbm_GBs_aggregate": args.rows * D * esize / (ms_step * 1e-3) / 1e9,
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "loader": load_info, "gpu_launches": int(launches),
             "parity_checked": parity_checked,
             "parity": {"planted_rows": planted, "what": "k copies of a query across every shard boundary returned exactly, "
                        "in row order" + ("; fused exchange == NCCL all-gather + merge, bit for bit" if world > 1 else "")},

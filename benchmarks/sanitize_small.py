@@ -29,7 +29,8 @@ def main():
         ix.close()
     ix = pkg.ResidentIndex.from_f32(rows, dtype="bf16")
     for mode, pair in (("ss", "0"), ("ts", "0"), ("ts", "1")):
-        os.environ["MMR_UMMA_MODE"], os.environ["MMR_UMMA_PAIR"] = mode, pair
+        pkg._native.set_option("MMR_UMMA_MODE", mode)
+        pkg._native.set_option("MMR_UMMA_PAIR", pair)
         for b in (5, 130):
             q = torch.from_numpy(util.queries(b, 512)).cuda()
             s, r = ix.search(q, 10)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MMR_ABI_VERSION 1
+#define MMR_ABI_VERSION 2
 
 enum mmr_status {
   MMR_OK = 0,
@@ -46,6 +46,11 @@ enum mmr_dtype {
   MMR_F16 = 2
 };
 
+enum mmr_query_precision {
+  MMR_QP_AUTO = 0, /* batches of >= 3 queries on one row range run on the tensor cores with 16-bit queries */
+  MMR_QP_F32 = 1   /* every query is scored in fp32 (K1 family): a request's result is independent of its batch */
+};
+
 #define MMR_MAX_K 64 /* INDEX_TOPK_TEXT defaults to 50, INDEX_TOPK_IMG to 12 (reference config.py:46-47) */
 
 typedef struct mmr_index mmr_index;
@@ -53,6 +58,11 @@ typedef struct mmr_index mmr_index;
 /* Library / error plumbing. */
 int mmr_abi_version(void);
 const char* mmr_last_error(void);
+/* Switches (MMR_PDL, MMR_UMMA_MODE, MMR_UMMA_PAIR, MMR_UMMA_NOPROBE, MMR_FORCE_FAMILY, MMR_UMMA_QUAD).  The
+ * environment is read once when the library is loaded; these change / read a switch afterwards (value NULL or "" =
+ * default).  mmr_get_option returns -1 for an unknown name. */
+int mmr_set_option(const char* name, const char* value);
+int mmr_get_option(const char* name);
 
 /*
  * Resident index over caller-owned device rows.
@@ -66,6 +76,10 @@ const char* mmr_last_error(void);
 int mmr_index_create(int device, int dim, int dtype, int64_t n_rows, const void* rows_dev,
                      const int64_t* seg_offsets_host, int32_t n_segments, int64_t row_base, mmr_index** out);
 int mmr_index_destroy(mmr_index* index);
+/* Query precision policy of this index (enum mmr_query_precision).  The serving store sets MMR_QP_F32 so that what a
+ * request gets never depends on which other requests shared its launch (the reference answers every request alone,
+ * app/ml/retrieve.py:103-117). */
+int mmr_index_set_query_precision(mmr_index* index, int mode);
 /* Re-point an existing handle at grown / rewritten rows after an upsert (same dim and dtype). */
 int mmr_index_update(mmr_index* index, int64_t n_rows, const void* rows_dev, const int64_t* seg_offsets_host,
                      int32_t n_segments);
@@ -101,6 +115,8 @@ int mmr_hash_strings(const uint8_t* data, const int32_t* offsets, int64_t n, uin
  *                   (the library leaves it reusable); not shared between concurrently running searches.
  */
 size_t mmr_search_workspace_bytes(const mmr_index* index, int32_t B, int32_t k);
+/* Exact size for mmr_search_ranges with n_ranges row ranges in total (mmr_search_workspace_bytes budgets 8 per query). */
+size_t mmr_search_ranges_workspace_bytes(const mmr_index* index, int32_t B, int32_t k, int64_t n_ranges);
 int mmr_search(const mmr_index* index, const float* queries_dev, const int32_t* query_seg_host, int32_t B,
                int32_t k, float* out_scores_dev, int64_t* out_rows_dev, void* workspace_dev, size_t workspace_bytes,
                void* stream);
@@ -108,14 +124,19 @@ int mmr_search(const mmr_index* index, const float* queries_dev, const int32_t* 
  * Same scan with explicit row ranges per query instead of one segment id: query b scans
  * ranges_host[2*r], ranges_host[2*r+1]) for r in [range_off_host[b], range_off_host[b+1]).  This is how a store that
  * appends delta segments between compactions (upsert = tombstone + append, lancedb_store.py:87-101) searches a tenant
- * that currently owns several ranges.  Rows overwritten with NaN (tombstones) never appear in results.
+ * that currently owns several ranges.  Rows overwritten with NaN (tombstones) never appear in results.  The ranges of
+ * one query must not overlap (MMR_ERR_INVALID).  Queries with identical range lists (the same tenant) are grouped four at
+ * a time and share one pass over those rows (K6); every score is computed in fp32 exactly as for a single query.
  */
 int mmr_search_ranges(const mmr_index* index, const float* queries_dev, int32_t B, int32_t k,
                       const int32_t* range_off_host, const int64_t* ranges_host, float* out_scores_dev,
                       int64_t* out_rows_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 /*
- * Same with HOST buffers: copies the queries in, scans, copies results out and synchronises the stream.
- * This is the call B200Store.search_* makes per request; its time is the end-to-end figure in bench.py.
+ * Same with HOST buffers; this is the call B200Store.search_* makes per request and its time is the end-to-end figure in
+ * bench.py.  Re-entrant (calls on one index take turns on its staging set).  For one or two queries on one row range the
+ * query travels in the kernel's parameters and the kernel writes the result and a completion flag into a mapped pinned
+ * mailbox the host spins on: one launch, no copies, no stream synchronisation.  Larger batches stage the queries with one
+ * H2D copy, the kernels still write into the mailbox, and the stream is synchronised.
  */
 int mmr_search_host(mmr_index* index, const float* queries_host, const int32_t* query_seg_host, int32_t B,
                     int32_t k, float* out_scores_host, int64_t* out_rows_host, void* stream);
@@ -148,6 +169,28 @@ int mmr_search_exchange(const mmr_index* index, const float* queries_dev, const 
                         int32_t k, const uint64_t* peer_bufs_host, int32_t G, int32_t rank, uint32_t seq,
                         float* out_scores_dev, int64_t* out_rows_dev, void* workspace_dev, size_t workspace_bytes,
                         void* stream);
+
+/* The same exchange with HOST buffers, for one process per GPU: for B <= 2 the query rides in the scan kernel's
+ * parameters, the wait+merge kernel writes the merged result and a completion flag into the index's mapped mailbox and
+ * the host spins on it (no H2D / D2H copies, no stream synchronisation on the request path). */
+int mmr_search_exchange_host(mmr_index* index, const float* queries_host, const int32_t* query_seg_host, int32_t B,
+                             int32_t k, const uint64_t* peer_bufs_host, int32_t G, int32_t rank, uint32_t seq,
+                             float* out_scores_host, int64_t* out_rows_host, void* stream);
+
+/*
+ * One process, G GPUs: the shape of the reference's deployment (ONE store object in ONE process, app/ml/retrieve.py:21)
+ * on a multi-GPU box.  `shards[g]` is a row-range shard on its own device (row_base = its first global row; shard 0's
+ * device collects).  A search runs one scan launch per device from per-device launcher threads; every scan kernel stores
+ * its [B, k] result into the collector's exchange buffer over NVLink peer mappings, the collector's wait+merge kernel
+ * writes the merged result and a completion flag into a mapped host mailbox.  Ranges are GLOBAL row ranges
+ * (mmr_search_ranges convention); each shard scans its slice of them.  Results equal the single-GPU scan bit for bit.
+ */
+typedef struct mmr_multi mmr_multi;
+int mmr_multi_create(mmr_index** shards, int32_t G, mmr_multi** out);
+int mmr_multi_destroy(mmr_multi* multi);
+int mmr_multi_search_host(mmr_multi* multi, const float* queries_host, int32_t B, int32_t k,
+                          const int32_t* range_off_host, const int64_t* ranges_host, float* out_scores_host,
+                          int64_t* out_rows_host);
 
 /*
  * Fusion + gate (K5): _fuse_results with no rerank scores (reference app/ml/retrieve.py:158-195) and

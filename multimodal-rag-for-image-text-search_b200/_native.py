@@ -11,13 +11,19 @@ LIB_PATH = os.environ.get("MMR_LIB_PATH") or os.path.join(HERE, "libmmr_b200.so"
 MMR_OK = 0
 MMR_BF16, MMR_F32, MMR_F16 = 0, 1, 2
 MMR_MAX_K = 64
-ABI_VERSION = 1
+ABI_VERSION = 2
+MMR_QP_AUTO, MMR_QP_F32 = 0, 1
 
 # every symbol include/mmr_b200.h declares: (name, restype, argtypes)
 _i32, _i64, _sz, _p, _f64 = C.c_int32, C.c_int64, C.c_size_t, C.c_void_p, C.c_double
 SYMBOLS = [
     ("mmr_abi_version", C.c_int, []),
     ("mmr_last_error", C.c_char_p, []),
+    ("mmr_set_option", C.c_int, [C.c_char_p, C.c_char_p]),
+    ("mmr_get_option", C.c_int, [C.c_char_p]),
+    ("mmr_index_set_query_precision", C.c_int, [_p, C.c_int]),
+    ("mmr_search_ranges_workspace_bytes", _sz, [_p, _i32, _i32, _i64]),
+    ("mmr_search_exchange_host", C.c_int, [_p, _p, _p, _i32, _i32, _p, _i32, _i32, C.c_uint32, _p, _p, _p]),
     ("mmr_index_create", C.c_int, [C.c_int, C.c_int, C.c_int, _i64, _p, _p, _i32, _i64, C.POINTER(_p)]),
     ("mmr_index_destroy", C.c_int, [_p]),
     ("mmr_index_update", C.c_int, [_p, _i64, _p, _p, _i32]),
@@ -34,6 +40,9 @@ SYMBOLS = [
     ("mmr_exchange_buffer_bytes", _sz, [_i32, _i32, _i32]),
     ("mmr_search_exchange_workspace_bytes", _sz, [_p, _i32, _i32]),
     ("mmr_search_exchange", C.c_int, [_p, _p, _p, _i32, _i32, _p, _i32, _i32, C.c_uint32, _p, _p, _p, _sz, _p]),
+    ("mmr_multi_create", C.c_int, [_p, _i32, C.POINTER(_p)]),
+    ("mmr_multi_destroy", C.c_int, [_p]),
+    ("mmr_multi_search_host", C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _p]),
     ("mmr_fuse", C.c_int, [_p, _p, _i32, _p, _p, _i32, _i32, _i32, _f64, _p, _p, _p, _p, _p, _p]),
     ("mmr_fuse_f64", C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _f64, _p, _p, _p, _p]),
     ("mmr_debug_umma_scores", C.c_int, [_p, _p, _i32, _i64, _i64, _p, _i64, _p, _sz, _p]),
@@ -74,3 +83,12 @@ def check(status: int) -> None:
     if status != MMR_OK:
         msg = lib().mmr_last_error()
         raise NativeError(f"mmr status {status}: {msg.decode() if msg else '?'}")
+
+
+def set_option(name: str, value) -> None:
+    """Change a library switch (MMR_PDL, MMR_UMMA_MODE, ...) after load; None restores the default."""
+    check(lib().mmr_set_option(name.encode(), None if value is None else str(value).encode()))
+
+
+def get_option(name: str) -> int:
+    return int(lib().mmr_get_option(name.encode()))

@@ -141,13 +141,37 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 }
 
 template <int KPL>
+__device__ __forceinline__ void merge_wait_body(const uint8_t* __restrict__ xbuf, int parity, uint32_t seq,
+                                                uint32_t wire_bytes, uint32_t score_bytes, int G, int B, int k,
+                                                float* __restrict__ out_scores, int64_t* __restrict__ out_rows,
+                                                uint64_t timeout_ns, int qi, int lane);
+
+template <int KPL>
 __global__ void merge_wait_kernel(const uint8_t* __restrict__ xbuf, int parity, uint32_t seq, uint32_t wire_bytes,
                                   uint32_t score_bytes, int G, int B, int k, float* __restrict__ out_scores,
-                                  int64_t* __restrict__ out_rows, uint64_t timeout_ns) {
+                                  int64_t* __restrict__ out_rows, uint64_t timeout_ns, uint32_t* done_flag,
+                                  uint32_t done_seq) {
   const int lane = threadIdx.x & 31;
   const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   // let the next search's scan start while we wait for the peers (it uses the other slot parity)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (done_flag != nullptr) {
+    // single-block form (B <= 4, host-buffer calls): out_* are mapped host memory; once every warp has written its
+    // result the block releases the completion flag at system scope and the host stops spinning
+    merge_wait_body<KPL>(xbuf, parity, seq, wire_bytes, score_bytes, G, B, k, out_scores, out_rows, timeout_ns, qi, lane);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(done_flag), "r"(done_seq) : "memory");
+    return;
+  }
+  merge_wait_body<KPL>(xbuf, parity, seq, wire_bytes, score_bytes, G, B, k, out_scores, out_rows, timeout_ns, qi, lane);
+}
+
+template <int KPL>
+__device__ __forceinline__ void merge_wait_body(const uint8_t* __restrict__ xbuf, int parity, uint32_t seq,
+                                                uint32_t wire_bytes, uint32_t score_bytes, int G, int B, int k,
+                                                float* __restrict__ out_scores, int64_t* __restrict__ out_rows,
+                                                uint64_t timeout_ns, int qi, int lane) {
   if (qi >= B) return;
   const uint32_t* flags = reinterpret_cast<const uint32_t*>(xbuf) + parity * MMR_XCHG_MAX_PEERS;
   bool ok = true;

@@ -41,6 +41,23 @@ __host__ __device__ __forceinline__ uint64_t make_key(float score, uint32_t row)
 __host__ __device__ __forceinline__ float key_score(uint64_t key) { return f32_from_orderable(uint32_t(key >> 32)); }
 __host__ __device__ __forceinline__ uint32_t key_row(uint64_t key) { return 0xFFFFFFFFu - uint32_t(key); }
 
+// ------------------------------------------------------------------------------------------------
+// Switches.  Read ONCE from the environment when the library is loaded; mmr_set_option() changes them
+// afterwards (tests, bench).  Nothing on the search path calls getenv.
+// ------------------------------------------------------------------------------------------------
+struct Options {
+  int pdl = 0;            // MMR_PDL=1        pipelined launches (programmatic dependent launch) for K1 / merge_wait
+  int umma_mode = 0;      // MMR_UMMA_MODE    0 = by batch size, 1 = ss, 2 = ts
+  int umma_pair = 1;      // MMR_UMMA_PAIR=0  single CTAs instead of CTA pairs
+  int umma_noprobe = 0;   // MMR_UMMA_NOPROBE=1
+  int force_family = 0;   // MMR_FORCE_FAMILY 1 = K1, 2 = K2 regardless of batch size
+  int umma_quad = 1;      // MMR_UMMA_QUAD=0  no 4-CTA multicast clusters
+};
+inline Options& options() {
+  static Options o;
+  return o;
+}
+
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------------
 // Warp helpers

@@ -4,13 +4,20 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include "aux_kernels.cuh"
 #include "common.cuh"
@@ -52,13 +59,17 @@ struct mmr_index {
   int64_t row_base = 0;
   std::vector<int64_t> seg;  // [n_segments + 1]
   int sm_count = 0;
-  // small staging for mmr_search_host
+  int query_precision = MMR_QP_AUTO;
+  // Host-buffer calls (mmr_search_host & co): one staging set per index, serialised by host_mu.
+  //   h_q / d_q      pinned + device copy of the queries (only when they do not ride in the kernel parameters)
+  //   h_box / d_box  MAPPED pinned mailbox: [flag u32 | pad to 64][scores f32 B*k | pad][rows i64 B*k]; the kernels write
+  //                  results and the completion flag straight into it, the host spins on the flag
+  std::mutex host_mu;
   float* h_q = nullptr;
   float* d_q = nullptr;
-  float* d_scores = nullptr;
-  int64_t* d_rows = nullptr;
-  float* h_scores = nullptr;
-  int64_t* h_rows = nullptr;
+  uint8_t* h_box = nullptr;
+  uint8_t* d_box = nullptr;
+  uint32_t box_seq = 0;
   void* d_ws = nullptr;
   size_t ws_bytes = 0;
   int cap_b = 0, cap_k = 0;
@@ -81,6 +92,50 @@ static int set_segments(mmr_index* ix, const int64_t* seg, int32_t nseg) {
   for (int i = 0; i < nseg; ++i)
     if (ix->seg[i] > ix->seg[i + 1]) return fail(MMR_ERR_INVALID, "segment offsets must be ascending");
   return MMR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ options
+static int* option_slot(const char* name) {
+  Options& o = options();
+  if (!name) return nullptr;
+  if (!strcmp(name, "MMR_PDL")) return &o.pdl;
+  if (!strcmp(name, "MMR_UMMA_MODE")) return &o.umma_mode;
+  if (!strcmp(name, "MMR_UMMA_PAIR")) return &o.umma_pair;
+  if (!strcmp(name, "MMR_UMMA_NOPROBE")) return &o.umma_noprobe;
+  if (!strcmp(name, "MMR_FORCE_FAMILY")) return &o.force_family;
+  if (!strcmp(name, "MMR_UMMA_QUAD")) return &o.umma_quad;
+  return nullptr;
+}
+static int parse_option(const char* name, const char* v, int dflt) {
+  if (!v || !v[0]) return dflt;
+  if (!strcmp(name, "MMR_UMMA_MODE")) return v[0] == 's' ? 1 : (v[0] == 't' ? 2 : 0);
+  return atoi(v);
+}
+static const char* kOptionNames[] = {"MMR_PDL", "MMR_UMMA_MODE", "MMR_UMMA_PAIR", "MMR_UMMA_NOPROBE", "MMR_FORCE_FAMILY",
+                                     "MMR_UMMA_QUAD"};
+namespace {
+struct OptionsFromEnv {  // the environment is read once, when the library is loaded
+  OptionsFromEnv() {
+    for (const char* name : kOptionNames) {
+      int* slot = option_slot(name);
+      *slot = parse_option(name, getenv(name), *slot);
+    }
+  }
+} g_options_from_env;
+}  // namespace
+
+extern "C" int mmr_set_option(const char* name, const char* value) {
+  int* slot = option_slot(name);
+  if (!slot) return fail(MMR_ERR_INVALID, "unknown option %s", name ? name : "(null)");
+  Options defaults;
+  Options& o = options();
+  const int dflt = *(reinterpret_cast<int*>(&defaults) + (slot - reinterpret_cast<int*>(&o)));
+  *slot = parse_option(name, value, dflt);
+  return MMR_OK;
+}
+extern "C" int mmr_get_option(const char* name) {
+  int* slot = option_slot(name);
+  return slot ? *slot : -1;
 }
 
 extern "C" int mmr_abi_version(void) { return MMR_ABI_VERSION; }
@@ -144,14 +199,11 @@ extern "C" int mmr_index_update(mmr_index* ix, int64_t n_rows, const void* rows_
 
 static void free_staging(mmr_index* ix) {
   if (ix->h_q) cudaFreeHost(ix->h_q);
-  if (ix->h_scores) cudaFreeHost(ix->h_scores);
-  if (ix->h_rows) cudaFreeHost(ix->h_rows);
+  if (ix->h_box) cudaFreeHost(ix->h_box);
   if (ix->d_q) cudaFree(ix->d_q);
-  if (ix->d_scores) cudaFree(ix->d_scores);
-  if (ix->d_rows) cudaFree(ix->d_rows);
   if (ix->d_ws) cudaFree(ix->d_ws);
-  ix->h_q = ix->d_q = ix->d_scores = ix->h_scores = nullptr;
-  ix->h_rows = ix->d_rows = nullptr;
+  ix->h_q = ix->d_q = nullptr;
+  ix->h_box = ix->d_box = nullptr;
   ix->d_ws = nullptr;
   ix->cap_b = ix->cap_k = 0;
 }
@@ -161,6 +213,13 @@ extern "C" int mmr_index_destroy(mmr_index* ix) {
   cudaSetDevice(ix->device);
   free_staging(ix);
   delete ix;
+  return MMR_OK;
+}
+
+extern "C" int mmr_index_set_query_precision(mmr_index* ix, int mode) {
+  if (!ix) return fail(MMR_ERR_INVALID, "index is NULL");
+  if (mode != MMR_QP_AUTO && mode != MMR_QP_F32) return fail(MMR_ERR_INVALID, "unknown query precision %d", mode);
+  ix->query_precision = mode;
   return MMR_OK;
 }
 
@@ -302,8 +361,6 @@ extern "C" int mmr_hash_strings(const uint8_t* data, const int32_t* offsets, int
 }
 
 // ------------------------------------------------------------------------------------------------ K1 launch
-typedef void (*stream_kernel_t)(const StreamParams);
-
 template <typename E, int D, int NQ, int KPL>
 static int launch_stream_t(const StreamParams& p, int grid, cudaStream_t st) {
   using C = StreamCfg<E, D, NQ, KPL>;
@@ -325,8 +382,7 @@ static int launch_stream_t(const StreamParams& p, int grid, cudaStream_t st) {
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  const char* pdl = getenv("MMR_PDL");
-  attr[0].val.programmaticStreamSerializationAllowed = (p.items == nullptr && pdl && pdl[0] == '1') ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = (p.items == nullptr && options().pdl) ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   CUDA_TRY(cudaLaunchKernelEx(&cfg, scan_stream_kernel<E, D, NQ, KPL>, p));
@@ -359,32 +415,42 @@ static int launch_stream(const mmr_index* ix, const StreamParams& p, int nq_pad,
   return fail(MMR_ERR_UNSUPPORTED, "no stream kernel for dtype %d dim %d", ix->dtype, ix->dim);
 }
 
-static int rows_per_stage(int) { return MMR_K1_ROWS; }
-
 // ------------------------------------------------------------------------------------------------ planning
 // Workspace layout (bytes):
 //   [0, 256)                          control block (ticket counter at +0)
-//   [256, 256 + PART)                 partial top-k keys  (uniform: grid*4*k u64; varlen: n_items*k u64)
-//   then (varlen only)                ScanItem[n_items], int32 item_off[B+1]
+//   [256, 256 + PART)                 partial top-k keys  (uniform: grid*8*k u64; varlen: n_items*K1_ITEM_NQ*k u64)
+//   then (varlen only)                ScanItem[n_items], QuerySlot[B]
+//   last                              the K2 slice (umma_workspace_bytes)
 static constexpr size_t WS_CTRL = 256;
 static constexpr int VARLEN_ITEMS_PER_WARP = 8;
+static constexpr int RANGES_PER_QUERY_BUDGET = 8;  // = B200Store's MAX_RANGES: a tenant is compacted before it owns more
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static int max_varlen_items(const mmr_index* ix, int B) { return ix->sm_count * K1_NW * VARLEN_ITEMS_PER_WARP + 2 * B + 64; }
+// Upper bound of the varlen plan: ~VARLEN_ITEMS_PER_WARP pieces per warp plus one (possibly short) piece per row range.
+static int64_t varlen_item_cap(const mmr_index* ix, int64_t n_ranges) {
+  return int64_t(ix->sm_count) * K1_NW * VARLEN_ITEMS_PER_WARP + n_ranges + 64;
+}
 
-extern "C" size_t mmr_search_workspace_bytes(const mmr_index* ix, int32_t B, int32_t k) {
+static size_t workspace_bytes_for(const mmr_index* ix, int32_t B, int32_t k, int64_t n_ranges) {
   if (!ix || B <= 0 || k <= 0) return 0;
   const size_t kk = size_t(std::min<int32_t>(k, MMR_MAX_K));
   const size_t uniform = size_t(ix->sm_count) * 8 * kk * 8;
-  const size_t items = size_t(max_varlen_items(ix, B));
-  const size_t varlen = align_up(items * kk * 8, 256) + align_up(items * sizeof(ScanItem), 256) +
-                        align_up(size_t(B + 1) * 4, 256);
+  const size_t items = size_t(varlen_item_cap(ix, n_ranges));
+  const size_t varlen = align_up(items * K1_ITEM_NQ * kk * 8, 256) + align_up(items * sizeof(ScanItem), 256) +
+                        align_up(size_t(B) * sizeof(QuerySlot), 256);
   size_t total = WS_CTRL + align_up(std::max(uniform, varlen), 256);
 #ifdef MMR_WITH_UMMA
   total += umma_workspace_bytes(ix->sm_count, ix->dim, B, int(kk));
 #endif
   return total;
+}
+
+extern "C" size_t mmr_search_workspace_bytes(const mmr_index* ix, int32_t B, int32_t k) {
+  return workspace_bytes_for(ix, B, k, int64_t(RANGES_PER_QUERY_BUDGET) * std::max(B, 0));
+}
+extern "C" size_t mmr_search_ranges_workspace_bytes(const mmr_index* ix, int32_t B, int32_t k, int64_t n_ranges) {
+  return workspace_bytes_for(ix, B, k, std::max<int64_t>(n_ranges, 0));
 }
 
 struct ExchangeInfo {  // fused push by K1's last CTA (only when one launch covers all B queries)
@@ -395,20 +461,37 @@ struct ExchangeInfo {  // fused push by K1's last CTA (only when one launch cove
   uint64_t flag[MMR_MAX_PEERS] = {};
 };
 
-static int search_uniform_stream(const mmr_index* ix, const float* q, int B, int k, uint32_t r0, uint32_t r1,
+struct QuerySrc {   // where the fp32 queries are: device memory, or host memory to be carried in the kernel parameters
+  const float* dev = nullptr;
+  const float* host = nullptr;
+};
+struct Completion {  // optional mailbox flag (mapped host memory) released by the kernel that writes the final result
+  uint32_t* flag_dev = nullptr;
+  uint32_t seq = 0;
+  bool armed = false;  // set by the launcher when the flag will really be written (single-launch paths only)
+};
+
+static int k1_group(const mmr_index* ix) { return ix->dtype == MMR_F32 ? 8 : 4; }  // queries per pass
+
+static bool can_inline(const mmr_index* ix, int B) { return B * ix->dim <= K1_INLINE_FLOATS && B <= 2; }
+
+static int search_uniform_stream(const mmr_index* ix, QuerySrc q, int B, int k, uint32_t r0, uint32_t r1,
                                  float* out_s, int64_t* out_r, uint8_t* ws, cudaStream_t st,
-                                 const ExchangeInfo* xi = nullptr) {
+                                 const ExchangeInfo* xi = nullptr, Completion* done = nullptr) {
   const int kpl = k <= 32 ? 1 : 2;
-  const int R = rows_per_stage(ix->dtype);
+  const int R = MMR_K1_ROWS;
   const int64_t nchunks = (int64_t(r1) - r0 + R - 1) / R;
   int grid = int(std::min<int64_t>(ix->sm_count, std::max<int64_t>(1, (nchunks + K1_NW - 1) / K1_NW)));
-  const int group = ix->dtype == MMR_F32 ? 8 : 4;  // queries per pass
+  const int group = k1_group(ix);
+  if (q.dev == nullptr && !(q.host && can_inline(ix, B))) return fail(MMR_ERR_INVALID, "queries must be device-resident for this batch size");
   for (int q0 = 0; q0 < B; q0 += group) {
     const int nq = std::min(group, B - q0);
     const int nq_pad = nq <= 2 ? nq : (nq <= 4 ? 4 : 8);
-    StreamParams p{};
+    StreamParams p;
+    memset(&p, 0, offsetof(StreamParams, qinline));
     p.rows = ix->rows;
-    p.queries = q;
+    p.queries = q.dev;
+    if (q.dev == nullptr) memcpy(p.qinline, q.host, size_t(B) * ix->dim * sizeof(float));
     p.q_first = q0;
     p.nq = nq;
     p.k = k;
@@ -419,15 +502,20 @@ static int search_uniform_stream(const mmr_index* ix, const float* q, int B, int
     p.out_scores = out_s;
     p.out_rows = out_r;
     p.row_base = ix->row_base;
-    p.items = nullptr;
-    p.n_items = 0;
-    if (xi && B <= group) {
-      p.n_peers = xi->n_peers;
-      p.seq = xi->seq;
-      p.wire_score_bytes = xi->wire_score_bytes;
-      for (int g = 0; g < xi->n_peers; ++g) {
-        p.peer_slot[g] = xi->slot[g];
-        p.peer_flag[g] = xi->flag[g];
+    if (B <= group) {  // one launch covers the batch: it may push to peers / ring the mailbox itself
+      if (xi) {
+        p.n_peers = xi->n_peers;
+        p.seq = xi->seq;
+        p.wire_score_bytes = xi->wire_score_bytes;
+        for (int g = 0; g < xi->n_peers; ++g) {
+          p.peer_slot[g] = xi->slot[g];
+          p.peer_flag[g] = xi->flag[g];
+        }
+      }
+      if (done && done->flag_dev) {
+        p.done_flag = done->flag_dev;
+        p.done_seq = done->seq;
+        done->armed = true;
       }
     }
     int rc = launch_stream(ix, p, nq_pad, kpl, grid, st);
@@ -437,54 +525,89 @@ static int search_uniform_stream(const mmr_index* ix, const float* q, int B, int
   return MMR_OK;
 }
 
-// `ranges[b]` = the row ranges query b scans (a tenant is one base segment plus any appended delta segments).
-static int search_varlen_stream(const mmr_index* ix, const float* q,
-                                const std::vector<std::vector<std::pair<uint32_t, uint32_t>>>& ranges, int k, float* out_s,
-                                int64_t* out_r, uint8_t* ws, size_t ws_bytes, cudaStream_t st) {
+// K6 -- the grouped varlen launch.  `ranges[b]` = the row ranges query b scans (a tenant is one base segment plus any
+// appended delta segments).  Queries with identical range lists (= the same tenant) are grouped K1_ITEM_NQ at a time, and
+// every work item is (one piece of one range, one query group): the rows of a tenant are read once per GROUP, not once
+// per query.  Scores are computed exactly as in the uniform K1 kernel (fp32 queries, same per-row
+// arithmetic), so a request's result does not depend on what it was batched with.
+typedef std::vector<std::pair<uint32_t, uint32_t>> RangeList;
+
+static int search_varlen_stream(const mmr_index* ix, const float* q, const std::vector<RangeList>& ranges, int k,
+                                float* out_s, int64_t* out_r, uint8_t* ws, size_t ws_bytes, cudaStream_t st) {
   const int B = int(ranges.size());
   const int kpl = k <= 32 ? 1 : 2;
-  const int R = rows_per_stage(ix->dtype);
-  int64_t total_rows = 0;
-  for (auto& rq : ranges)
-    for (auto& r : rq) total_rows += int64_t(r.second) - r.first;
+  const int R = MMR_K1_ROWS;
+  // 1. group the queries by range list (first-appearance order keeps the plan deterministic)
+  std::map<RangeList, int> tenant_of;
+  std::vector<std::vector<int>> members;
+  std::vector<const RangeList*> tenant_ranges;
+  for (int b = 0; b < B; ++b) {
+    auto it = tenant_of.find(ranges[b]);
+    if (it == tenant_of.end()) {
+      it = tenant_of.emplace(ranges[b], int(members.size())).first;
+      members.emplace_back();
+      tenant_ranges.push_back(&it->first);
+    }
+    members[it->second].push_back(b);
+  }
+  // 2. size the pieces: about VARLEN_ITEMS_PER_WARP per warp over everything this launch reads
+  int64_t total_rows = 0, n_group_ranges = 0;
+  for (size_t t = 0; t < members.size(); ++t) {
+    const int64_t ngroups = (int64_t(members[t].size()) + K1_ITEM_NQ - 1) / K1_ITEM_NQ;
+    for (auto& r : *tenant_ranges[t]) total_rows += (int64_t(r.second) - r.first) * ngroups;
+    n_group_ranges += int64_t(tenant_ranges[t]->size()) * ngroups;
+  }
   const int twarps = ix->sm_count * K1_NW;
   const int64_t target = int64_t(twarps) * VARLEN_ITEMS_PER_WARP;
   int64_t item_rows = std::max<int64_t>(64, (total_rows + target - 1) / target);
   item_rows = (item_rows + R - 1) / R * R;
+  // 3. emit items and per-query slots
   std::vector<ScanItem> items;
-  std::vector<int32_t> off(B + 1, 0);
-  for (int b = 0; b < B; ++b) {
-    off[b] = int32_t(items.size());
-    for (auto& r : ranges[b]) {
-      for (int64_t s = r.first; s < int64_t(r.second); s += item_rows) {
-        ScanItem it;
-        it.row_begin = uint32_t(s);
-        it.row_end = uint32_t(std::min<int64_t>(s + item_rows, r.second));
-        it.query = b;
-        it.pad = 0;
-        items.push_back(it);
+  std::vector<QuerySlot> slots(B);
+  items.reserve(size_t(std::min<int64_t>(target + n_group_ranges, 1 << 22)));
+  for (size_t t = 0; t < members.size(); ++t) {
+    const std::vector<int>& m = members[t];
+    for (size_t g0 = 0; g0 < m.size(); g0 += K1_ITEM_NQ) {
+      const int nq = int(std::min<size_t>(K1_ITEM_NQ, m.size() - g0));
+      const int item0 = int(items.size());
+      for (auto& r : *tenant_ranges[t]) {
+        for (int64_t s = r.first; s < int64_t(r.second); s += item_rows) {
+          ScanItem it;
+          it.row_begin = uint32_t(s);
+          it.row_end = uint32_t(std::min<int64_t>(s + item_rows, r.second));
+          for (int j = 0; j < K1_ITEM_NQ; ++j) it.query[j] = m[g0 + std::min(j, nq - 1)];
+          it.nq = nq;
+          it.pad = 0;
+          items.push_back(it);
+        }
       }
+      for (int j = 0; j < nq; ++j) slots[m[g0 + j]] = QuerySlot{item0, int(items.size()) - item0, j, 0};
     }
   }
-  off[B] = int32_t(items.size());
   const int n_items = int(items.size());
-  if (n_items > max_varlen_items(ix, B)) return fail(MMR_ERR_WORKSPACE, "varlen plan produced %d items (too many row ranges)", n_items);
-  const size_t part_bytes = align_up(size_t(std::max(n_items, 1)) * k * 8, 256);
+  const size_t part_bytes = align_up(size_t(std::max(n_items, 1)) * K1_ITEM_NQ * k * 8, 256);
   const size_t item_bytes = align_up(size_t(std::max(n_items, 1)) * sizeof(ScanItem), 256);
-  const size_t off_bytes = align_up(size_t(B + 1) * 4, 256);
-  if (WS_CTRL + part_bytes + item_bytes + off_bytes > ws_bytes) return fail(MMR_ERR_WORKSPACE, "workspace too small");
+  const size_t slot_bytes = align_up(size_t(B) * sizeof(QuerySlot), 256);
+  size_t k2_bytes = 0;
+#ifdef MMR_WITH_UMMA
+  k2_bytes = umma_workspace_bytes(ix->sm_count, ix->dim, B, k);
+#endif
+  if (WS_CTRL + part_bytes + item_bytes + slot_bytes + k2_bytes > ws_bytes)
+    return fail(MMR_ERR_WORKSPACE,
+                "workspace too small for %d work items over %lld row ranges: size it with "
+                "mmr_search_ranges_workspace_bytes(index, B, k, n_ranges)", n_items, (long long)n_group_ranges);
   uint64_t* d_part = reinterpret_cast<uint64_t*>(ws + WS_CTRL);
   ScanItem* d_items = reinterpret_cast<ScanItem*>(ws + WS_CTRL + part_bytes);
-  int32_t* d_off = reinterpret_cast<int32_t*>(ws + WS_CTRL + part_bytes + item_bytes);
+  QuerySlot* d_slots = reinterpret_cast<QuerySlot*>(ws + WS_CTRL + part_bytes + item_bytes);
+  // pageable sources: cudaMemcpyAsync stages them before returning, the vectors may die after this call
   if (n_items > 0) CUDA_TRY(cudaMemcpyAsync(d_items, items.data(), size_t(n_items) * sizeof(ScanItem), cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(d_off, off.data(), size_t(B + 1) * 4, cudaMemcpyHostToDevice, st));
-  // pageable sources: the copies above are staged before returning, the vectors may die after this call
+  CUDA_TRY(cudaMemcpyAsync(d_slots, slots.data(), size_t(B) * sizeof(QuerySlot), cudaMemcpyHostToDevice, st));
   if (n_items > 0) {
-    StreamParams p{};
+    StreamParams p;
+    memset(&p, 0, offsetof(StreamParams, qinline));
     p.rows = ix->rows;
     p.queries = q;
-    p.q_first = 0;
-    p.nq = 1;
+    p.nq = K1_ITEM_NQ;
     p.k = k;
     p.partial = d_part;
     p.ticket = reinterpret_cast<unsigned int*>(ws);
@@ -492,123 +615,158 @@ static int search_varlen_stream(const mmr_index* ix, const float* q,
     p.items = d_items;
     p.n_items = n_items;
     const int grid = int(std::min<int64_t>(ix->sm_count, (n_items + K1_NW - 1) / K1_NW));
-    int rc = launch_stream(ix, p, 1, kpl, grid, st);
+    int rc = launch_stream(ix, p, K1_ITEM_NQ, kpl, grid, st);
     if (rc != MMR_OK) return rc;
   }
   const int wpb = 4;
   if (kpl == 1)
-    merge_items_kernel<1><<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(d_part, d_off, B, k, out_s, out_r, ix->row_base);
+    merge_items_kernel<1><<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(d_part, d_slots, B, K1_ITEM_NQ, k, out_s, out_r, ix->row_base);
   else
-    merge_items_kernel<2><<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(d_part, d_off, B, k, out_s, out_r, ix->row_base);
+    merge_items_kernel<2><<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(d_part, d_slots, B, K1_ITEM_NQ, k, out_s, out_r, ix->row_base);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   g_last_kernel = 3;
   return MMR_OK;
 }
 
-extern "C" int mmr_search(const mmr_index* ix, const float* queries_dev, const int32_t* query_seg_host, int32_t B,
-                          int32_t k, float* out_scores_dev, int64_t* out_rows_dev, void* workspace_dev,
-                          size_t workspace_bytes, void* stream) {
+// One shared row range for the whole batch: K2 when allowed and preferred, else K1 passes.
+static int search_uniform(const mmr_index* ix, QuerySrc q, int B, int k, uint32_t r0, uint32_t r1, float* out_s,
+                          int64_t* out_r, uint8_t* ws, size_t ws_total, cudaStream_t st, const ExchangeInfo* xi = nullptr,
+                          Completion* done = nullptr) {
+#ifdef MMR_WITH_UMMA
+  if (q.dev != nullptr && ix->query_precision == MMR_QP_AUTO &&
+      umma_preferred(ix->dtype, ix->dim, B, k, int64_t(r1) - r0)) {
+    int rc = umma_search(ix->umma, ix->umma2, ix->rows, ix->n_rows, ix->dim, ix->dtype, ix->sm_count, q.dev, B, k, r0, r1,
+                         ix->row_base, out_s, out_r, ws + ws_total - umma_workspace_bytes(ix->sm_count, ix->dim, B, k), st,
+                         g_err);
+    if (rc == MMR_OK) {
+      g_launches += umma_launches_per_search();
+      g_last_kernel = 2;
+    }
+    return rc;
+  }
+#endif
+  return search_uniform_stream(ix, q, B, k, r0, r1, out_s, out_r, ws, st, xi, done);
+}
+
+// true when a uniform batch of B queries would run on the tensor-core family
+static bool uniform_takes_k2(const mmr_index* ix, int B, int k, int64_t nrows) {
+#ifdef MMR_WITH_UMMA
+  return ix->query_precision == MMR_QP_AUTO && umma_preferred(ix->dtype, ix->dim, B, k, nrows);
+#else
+  return false;
+#endif
+}
+
+static int check_search_args(const mmr_index* ix, int32_t B, int32_t k) {
   if (!ix) return fail(MMR_ERR_INVALID, "index is NULL");
   if (B <= 0) return fail(MMR_ERR_INVALID, "B must be >= 1");
   if (k < 1 || k > MMR_MAX_K) return fail(MMR_ERR_INVALID, "k must be in [1, %d]", MMR_MAX_K);
-  if (!queries_dev || !out_scores_dev || !out_rows_dev || !workspace_dev) return fail(MMR_ERR_INVALID, "NULL buffer");
-  if (workspace_bytes < mmr_search_workspace_bytes(ix, B, k)) return fail(MMR_ERR_WORKSPACE, "workspace too small");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
-  const int nseg = int(ix->seg.size()) - 1;
+  return MMR_OK;
+}
 
-  // row range of every query
-  std::vector<std::pair<uint32_t, uint32_t>> ranges(B);
-  bool uniform = true;
+// segment ids -> one range per query; `uniform` = everybody scans the same range
+static int ranges_from_segments(const mmr_index* ix, const int32_t* query_seg_host, int B, std::vector<RangeList>& out,
+                                bool& uniform) {
+  const int nseg = int(ix->seg.size()) - 1;
+  out.assign(B, RangeList(1));
+  uniform = true;
   for (int b = 0; b < B; ++b) {
     const int s = query_seg_host ? query_seg_host[b] : -1;
     if (s < -1 || s >= nseg) return fail(MMR_ERR_INVALID, "query %d: segment %d out of range [0, %d)", b, s, nseg);
-    ranges[b] = s < 0 ? std::make_pair(uint32_t(0), uint32_t(ix->n_rows))
+    out[b][0] = s < 0 ? std::make_pair(uint32_t(0), uint32_t(ix->n_rows))
                       : std::make_pair(uint32_t(ix->seg[s]), uint32_t(ix->seg[s + 1]));
-    if (ranges[b] != ranges[0]) uniform = false;
+    if (out[b][0] != out[0][0]) uniform = false;
   }
-  if (uniform) {
-#ifdef MMR_WITH_UMMA
-    if (umma_preferred(ix->dtype, ix->dim, B, k, int64_t(ranges[0].second) - ranges[0].first)) {
-      int rc = umma_search(ix->umma, ix->umma2, ix->rows, ix->n_rows, ix->dim, ix->dtype, ix->sm_count, queries_dev, B, k, ranges[0].first,
-                           ranges[0].second, ix->row_base, out_scores_dev, out_rows_dev,
-                           ws + mmr_search_workspace_bytes(ix, B, k) - umma_workspace_bytes(ix->sm_count, ix->dim, B, k),
-                           st, g_err);
-      if (rc == MMR_OK) {
-        g_launches += umma_launches_per_search();
-        g_last_kernel = 2;
-      }
-      return rc;
-    }
-#endif
-    return search_uniform_stream(ix, queries_dev, B, k, ranges[0].first, ranges[0].second, out_scores_dev,
-                                 out_rows_dev, ws, st);
-  }
-  std::vector<std::vector<std::pair<uint32_t, uint32_t>>> per_query(B);
-  for (int b = 0; b < B; ++b) per_query[b].push_back(ranges[b]);
-  return search_varlen_stream(ix, queries_dev, per_query, k, out_scores_dev, out_rows_dev, ws, workspace_bytes, st);
+  return MMR_OK;
+}
+
+extern "C" int mmr_search(const mmr_index* ix, const float* queries_dev, const int32_t* query_seg_host, int32_t B,
+                          int32_t k, float* out_scores_dev, int64_t* out_rows_dev, void* workspace_dev,
+                          size_t workspace_bytes, void* stream) {
+  int rc = check_search_args(ix, B, k);
+  if (rc != MMR_OK) return rc;
+  if (!queries_dev || !out_scores_dev || !out_rows_dev || !workspace_dev) return fail(MMR_ERR_INVALID, "NULL buffer");
+  const size_t need = workspace_bytes_for(ix, B, k, B);
+  if (workspace_bytes < need) return fail(MMR_ERR_WORKSPACE, "workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
+  std::vector<RangeList> ranges;
+  bool uniform = true;
+  rc = ranges_from_segments(ix, query_seg_host, B, ranges, uniform);
+  if (rc != MMR_OK) return rc;
+  QuerySrc q;
+  q.dev = queries_dev;
+  if (uniform)
+    return search_uniform(ix, q, B, k, ranges[0][0].first, ranges[0][0].second, out_scores_dev, out_rows_dev, ws,
+                          workspace_bytes, st);
+  return search_varlen_stream(ix, queries_dev, ranges, k, out_scores_dev, out_rows_dev, ws, workspace_bytes, st);
 }
 
 // Explicit row ranges per query: query b scans ranges[range_off[b] .. range_off[b+1]) (pairs of [begin, end) row
 // ordinals).  Used by stores that append delta segments between compactions.
-extern "C" int mmr_search_ranges(const mmr_index* ix, const float* queries_dev, int32_t B, int32_t k,
-                                 const int32_t* range_off_host, const int64_t* ranges_host, float* out_scores_dev,
-                                 int64_t* out_rows_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
-  if (!ix) return fail(MMR_ERR_INVALID, "index is NULL");
-  if (B <= 0) return fail(MMR_ERR_INVALID, "B must be >= 1");
-  if (k < 1 || k > MMR_MAX_K) return fail(MMR_ERR_INVALID, "k must be in [1, %d]", MMR_MAX_K);
-  if (!queries_dev || !range_off_host || !out_scores_dev || !out_rows_dev || !workspace_dev)
-    return fail(MMR_ERR_INVALID, "NULL buffer");
-  if (workspace_bytes < mmr_search_workspace_bytes(ix, B, k)) return fail(MMR_ERR_WORKSPACE, "workspace too small");
-  std::vector<std::vector<std::pair<uint32_t, uint32_t>>> per_query(B);
-  bool single_shared = true;
+static int parse_ranges(const mmr_index* ix, int B, const int32_t* range_off_host, const int64_t* ranges_host,
+                        std::vector<RangeList>& per_query, bool& single_shared) {
+  per_query.assign(B, RangeList());
+  single_shared = true;
   for (int b = 0; b < B; ++b) {
     if (range_off_host[b + 1] < range_off_host[b]) return fail(MMR_ERR_INVALID, "range offsets must be ascending");
     for (int32_t r = range_off_host[b]; r < range_off_host[b + 1]; ++r) {
       const int64_t lo = ranges_host[2 * r], hi = ranges_host[2 * r + 1];
-      if (lo < 0 || hi < lo || hi > ix->n_rows) return fail(MMR_ERR_INVALID, "query %d: bad row range [%lld, %lld)", b, (long long)lo, (long long)hi);
+      if (lo < 0 || hi < lo || hi > ix->n_rows)
+        return fail(MMR_ERR_INVALID, "query %d: bad row range [%lld, %lld)", b, (long long)lo, (long long)hi);
       if (hi > lo) per_query[b].push_back({uint32_t(lo), uint32_t(hi)});
     }
+    // a row must not be offered twice to one query (the warp top-k assumes distinct keys): reject overlapping ranges
+    RangeList sorted = per_query[b];
+    std::sort(sorted.begin(), sorted.end());
+    for (size_t i = 1; i < sorted.size(); ++i)
+      if (sorted[i].first < sorted[i - 1].second)
+        return fail(MMR_ERR_INVALID, "query %d: row ranges [%u, %u) and [%u, %u) overlap", b, sorted[i - 1].first,
+                    sorted[i - 1].second, sorted[i].first, sorted[i].second);
     if (per_query[b].size() != 1 || per_query[b] != per_query[0]) single_shared = false;
   }
+  return MMR_OK;
+}
+
+extern "C" int mmr_search_ranges(const mmr_index* ix, const float* queries_dev, int32_t B, int32_t k,
+                                 const int32_t* range_off_host, const int64_t* ranges_host, float* out_scores_dev,
+                                 int64_t* out_rows_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  int rc = check_search_args(ix, B, k);
+  if (rc != MMR_OK) return rc;
+  if (!queries_dev || !range_off_host || !out_scores_dev || !out_rows_dev || !workspace_dev)
+    return fail(MMR_ERR_INVALID, "NULL buffer");
+  if (workspace_bytes < workspace_bytes_for(ix, B, k, 0)) return fail(MMR_ERR_WORKSPACE, "workspace too small");
+  std::vector<RangeList> per_query;
+  bool single_shared = true;
+  rc = parse_ranges(ix, B, range_off_host, ranges_host, per_query, single_shared);
+  if (rc != MMR_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
-  if (single_shared) {  // everyone scans the same single range: the uniform kernels apply
-    const uint32_t r0 = per_query[0][0].first, r1 = per_query[0][0].second;
-#ifdef MMR_WITH_UMMA
-    if (umma_preferred(ix->dtype, ix->dim, B, k, int64_t(r1) - r0)) {
-      int rc = umma_search(ix->umma, ix->umma2, ix->rows, ix->n_rows, ix->dim, ix->dtype, ix->sm_count, queries_dev, B, k, r0, r1,
-                           ix->row_base, out_scores_dev, out_rows_dev,
-                           ws + mmr_search_workspace_bytes(ix, B, k) - umma_workspace_bytes(ix->sm_count, ix->dim, B, k),
-                           st, g_err);
-      if (rc == MMR_OK) {
-        g_launches += umma_launches_per_search();
-        g_last_kernel = 2;
-      }
-      return rc;
-    }
-#endif
-    return search_uniform_stream(ix, queries_dev, B, k, r0, r1, out_scores_dev, out_rows_dev, ws, st);
-  }
+  QuerySrc q;
+  q.dev = queries_dev;
+  if (single_shared)  // everyone scans the same single range: the uniform kernels apply
+    return search_uniform(ix, q, B, k, per_query[0][0].first, per_query[0][0].second, out_scores_dev, out_rows_dev, ws,
+                          workspace_bytes, st);
   return search_varlen_stream(ix, queries_dev, per_query, k, out_scores_dev, out_rows_dev, ws, workspace_bytes, st);
 }
 
-// Result staging is ONE buffer on each side ([scores f32 B*k | pad | rows i64 B*k]) so a search costs one D2H copy.
-static size_t staging_rows_off(int cb, int ck) { return align_up(size_t(cb) * ck * 4, 16); }
+// ------------------------------------------------------------------------------------------------ host-buffer calls
+// Mailbox layout inside h_box / d_box (mapped pinned memory, same bytes seen by both sides):
+static constexpr size_t BOX_HEADER = 64;
+static size_t box_rows_off(int B, int k) { return BOX_HEADER + align_up(size_t(B) * k * 4, 16); }
 
 static int ensure_staging(mmr_index* ix, int B, int k) {
   if (B <= ix->cap_b && k <= ix->cap_k) return MMR_OK;
   free_staging(ix);
   const int cb = std::max(B, 8), ck = std::max(k, 16);
-  const size_t res_bytes = staging_rows_off(cb, ck) + size_t(cb) * ck * 8;
+  const size_t box_bytes = box_rows_off(cb, ck) + size_t(cb) * ck * 8;
   CUDA_TRY(cudaMallocHost(&ix->h_q, size_t(cb) * ix->dim * 4));
-  CUDA_TRY(cudaMallocHost(&ix->h_scores, res_bytes));
   CUDA_TRY(cudaMalloc(&ix->d_q, size_t(cb) * ix->dim * 4));
-  CUDA_TRY(cudaMalloc(&ix->d_scores, res_bytes));
-  ix->h_rows = nullptr;  // views into the packed buffers are computed per call (they depend on B and k)
-  ix->d_rows = nullptr;
-  ix->ws_bytes = mmr_search_workspace_bytes(ix, cb, ck);
+  CUDA_TRY(cudaHostAlloc(&ix->h_box, box_bytes, cudaHostAllocMapped));
+  CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ix->d_box), ix->h_box, 0));
+  memset(ix->h_box, 0, box_bytes);
+  ix->ws_bytes = workspace_bytes_for(ix, cb, ck, int64_t(RANGES_PER_QUERY_BUDGET) * cb);
   CUDA_TRY(cudaMalloc(&ix->d_ws, ix->ws_bytes));
   CUDA_TRY(cudaMemset(ix->d_ws, 0, ix->ws_bytes));
   ix->cap_b = cb;
@@ -616,30 +774,86 @@ static int ensure_staging(mmr_index* ix, int B, int k) {
   return MMR_OK;
 }
 
+static inline void cpu_relax() {
+#if defined(__x86_64__)
+  _mm_pause();
+#endif
+}
+
+// Wait for the mailbox flag to reach `seq`.  The kernel releases it at system scope right after its result stores, so
+// the host sees the result a PCIe write later instead of after a stream synchronisation.  The stream is polled now and
+// then so that a faulted kernel turns into an error instead of an endless spin.
+static int wait_mailbox(mmr_index* ix, uint32_t seq, cudaStream_t st) {
+  volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(ix->h_box);
+  for (uint64_t spins = 1;; ++spins) {
+    if (*flag == seq) break;
+    if ((spins & 4095) == 0) {
+      cudaError_t e = cudaStreamQuery(st);
+      if (e == cudaSuccess) {
+        if (*flag == seq) break;
+        return fail(MMR_ERR_CUDA, "search finished without ringing its mailbox");
+      }
+      if (e != cudaErrorNotReady) return fail(MMR_ERR_CUDA, "search failed: %s", cudaGetErrorString(e));
+    }
+    cpu_relax();
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  return MMR_OK;
+}
+
+// Shared tail of the host-buffer calls: results are in the mailbox (written by the kernels through the mapped
+// pointer); wait (flag or stream), then hand them to the caller.
+static int finish_host_call(mmr_index* ix, const Completion& done, int B, int k, float* out_scores_host,
+                            int64_t* out_rows_host, cudaStream_t st) {
+  if (done.armed) {
+    int rc = wait_mailbox(ix, done.seq, st);
+    if (rc != MMR_OK) return rc;
+  } else {
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  memcpy(out_scores_host, ix->h_box + BOX_HEADER, size_t(B) * k * 4);
+  memcpy(out_rows_host, ix->h_box + box_rows_off(B, k), size_t(B) * k * 8);
+  return MMR_OK;
+}
+
 extern "C" int mmr_search_host(mmr_index* ix, const float* queries_host, const int32_t* query_seg_host, int32_t B,
                                int32_t k, float* out_scores_host, int64_t* out_rows_host, void* stream) {
-  if (!ix) return fail(MMR_ERR_INVALID, "index is NULL");
-  if (B <= 0) return fail(MMR_ERR_INVALID, "B must be >= 1");
-  if (k < 1 || k > MMR_MAX_K) return fail(MMR_ERR_INVALID, "k must be in [1, %d]", MMR_MAX_K);
+  int rc = check_search_args(ix, B, k);
+  if (rc != MMR_OK) return rc;
   if (!queries_host || !out_scores_host || !out_rows_host) return fail(MMR_ERR_INVALID, "NULL buffer");
+  std::lock_guard<std::mutex> guard(ix->host_mu);   // one staging set per index: concurrent callers take turns
   CUDA_TRY(cudaSetDevice(ix->device));
-  int rc = ensure_staging(ix, B, k);
+  rc = ensure_staging(ix, B, k);
   if (rc != MMR_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t rows_off = staging_rows_off(B, k);
-  const size_t res_bytes = rows_off + size_t(B) * k * 8;
-  uint8_t* d_res = reinterpret_cast<uint8_t*>(ix->d_scores);
-  uint8_t* h_res = reinterpret_cast<uint8_t*>(ix->h_scores);
-  memcpy(ix->h_q, queries_host, size_t(B) * ix->dim * 4);
-  CUDA_TRY(cudaMemcpyAsync(ix->d_q, ix->h_q, size_t(B) * ix->dim * 4, cudaMemcpyHostToDevice, st));
-  rc = mmr_search(ix, ix->d_q, query_seg_host, B, k, reinterpret_cast<float*>(d_res),
-                  reinterpret_cast<int64_t*>(d_res + rows_off), ix->d_ws, ix->ws_bytes, st);
+  std::vector<RangeList> ranges;
+  bool uniform = true;
+  rc = ranges_from_segments(ix, query_seg_host, B, ranges, uniform);
   if (rc != MMR_OK) return rc;
-  CUDA_TRY(cudaMemcpyAsync(h_res, d_res, res_bytes, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
-  memcpy(out_scores_host, h_res, size_t(B) * k * 4);
-  memcpy(out_rows_host, h_res + rows_off, size_t(B) * k * 8);
-  return MMR_OK;
+  float* box_s = reinterpret_cast<float*>(ix->d_box + BOX_HEADER);
+  int64_t* box_r = reinterpret_cast<int64_t*>(ix->d_box + box_rows_off(B, k));
+  Completion done;
+  done.flag_dev = reinterpret_cast<uint32_t*>(ix->d_box);
+  done.seq = ++ix->box_seq ? ix->box_seq : ++ix->box_seq;   // never 0
+  const uint32_t r0 = ranges[0][0].first, r1 = ranges[0][0].second;
+  if (uniform && can_inline(ix, B) && !uniform_takes_k2(ix, B, k, int64_t(r1) - r0)) {
+    // the latency path of a single request: ONE launch carries the query in its parameters, the kernel's last CTA
+    // writes the result and the flag into the mailbox -- no H2D copy, no D2H copy, no stream synchronisation
+    QuerySrc q;
+    q.host = queries_host;
+    rc = search_uniform_stream(ix, q, B, k, r0, r1, box_s, box_r, static_cast<uint8_t*>(ix->d_ws), st, nullptr, &done);
+  } else {
+    memcpy(ix->h_q, queries_host, size_t(B) * ix->dim * 4);
+    CUDA_TRY(cudaMemcpyAsync(ix->d_q, ix->h_q, size_t(B) * ix->dim * 4, cudaMemcpyHostToDevice, st));
+    QuerySrc q;
+    q.dev = ix->d_q;
+    if (uniform)
+      rc = search_uniform(ix, q, B, k, r0, r1, box_s, box_r, static_cast<uint8_t*>(ix->d_ws), ix->ws_bytes, st, nullptr, &done);
+    else
+      rc = search_varlen_stream(ix, ix->d_q, ranges, k, box_s, box_r, static_cast<uint8_t*>(ix->d_ws), ix->ws_bytes, st);
+  }
+  if (rc != MMR_OK) return rc;
+  return finish_host_call(ix, done, B, k, out_scores_host, out_rows_host, st);
 }
 
 // ------------------------------------------------------------------------------------------------ fused exchange
@@ -656,73 +870,59 @@ extern "C" size_t mmr_search_exchange_workspace_bytes(const mmr_index* ix, int32
   return base ? base + align_up(xchg_wire_bytes(B, std::min<int32_t>(k, MMR_MAX_K)), 256) : 0;
 }
 
-extern "C" int mmr_search_exchange(const mmr_index* ix, const float* queries_dev, const int32_t* query_seg_host,
-                                   int32_t B, int32_t k, const uint64_t* peer_bufs_host, int32_t G, int32_t rank,
-                                   uint32_t seq, float* out_scores_dev, int64_t* out_rows_dev, void* workspace_dev,
-                                   size_t workspace_bytes, void* stream) {
-  if (!ix) return fail(MMR_ERR_INVALID, "index is NULL");
-  if (!peer_bufs_host || G < 1 || G > MMR_XCHG_MAX_PEERS || rank < 0 || rank >= G)
-    return fail(MMR_ERR_INVALID, "bad peer table (G=%d, rank=%d)", G, rank);
-  if (seq == 0) return fail(MMR_ERR_INVALID, "seq must start at 1 and grow by 1 per search");
-  if (B <= 0 || k < 1 || k > MMR_MAX_K) return fail(MMR_ERR_INVALID, "bad B or k");
-  if (!queries_dev || !out_scores_dev || !out_rows_dev || !workspace_dev) return fail(MMR_ERR_INVALID, "NULL buffer");
-  const size_t base_ws = mmr_search_workspace_bytes(ix, B, k);
-  if (workspace_bytes < mmr_search_exchange_workspace_bytes(ix, B, k)) return fail(MMR_ERR_WORKSPACE, "workspace too small");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
+// The exchange proper.  push_mask: which peers receive this rank's result (bit g); do_merge: whether this rank waits for
+// all G slots and merges (every rank in the SPMD form; only the collecting device in the single-process form).
+// Exactly one of {per_query ranges, uniform range} describes what is scanned.
+static int exchange_impl(const mmr_index* ix, QuerySrc q, int B, int k, bool uniform, uint32_t r0, uint32_t r1,
+                         const std::vector<RangeList>* per_query, const uint64_t* peer_bufs, int G, int rank, uint32_t seq,
+                         uint32_t push_mask, bool do_merge, float* out_s, int64_t* out_r, uint8_t* ws, size_t base_ws,
+                         cudaStream_t st, Completion* done) {
   const uint32_t score_bytes = xchg_score_bytes(B, k), wire_bytes = xchg_wire_bytes(B, k);
   const int parity = int(seq & 1u);
   uint8_t* wire = ws + base_ws;  // this rank's own result, [scores | rows]
   float* w_scores = reinterpret_cast<float*>(wire);
   int64_t* w_rows = reinterpret_cast<int64_t*>(wire + score_bytes);
   ExchangeInfo xi;
-  xi.n_peers = G;
   xi.seq = seq;
   xi.wire_score_bytes = score_bytes;
   for (int g = 0; g < G; ++g) {
-    xi.slot[g] = peer_bufs_host[g] + MMR_XCHG_HEADER + (size_t(parity) * G + rank) * wire_bytes;
-    xi.flag[g] = peer_bufs_host[g] + (size_t(parity) * MMR_XCHG_MAX_PEERS + rank) * 4;
+    if (!(push_mask >> g & 1u)) continue;
+    xi.slot[xi.n_peers] = peer_bufs[g] + MMR_XCHG_HEADER + (size_t(parity) * G + rank) * wire_bytes;
+    xi.flag[xi.n_peers] = peer_bufs[g] + (size_t(parity) * MMR_XCHG_MAX_PEERS + rank) * 4;
+    ++xi.n_peers;
   }
   // 1. the shard-local scan
   bool pushed = false;
-  const int nseg = int(ix->seg.size()) - 1;
-  bool uniform = true;
-  int s0 = query_seg_host ? query_seg_host[0] : -1;
-  for (int b = 0; b < B && uniform; ++b) uniform = (query_seg_host ? query_seg_host[b] : -1) == s0;
-  if (s0 < -1 || s0 >= nseg) return fail(MMR_ERR_INVALID, "segment %d out of range", s0);
-  const uint32_t r0 = s0 < 0 ? 0u : uint32_t(ix->seg[s0]);
-  const uint32_t r1 = s0 < 0 ? uint32_t(ix->n_rows) : uint32_t(ix->seg[s0 + 1]);
-  bool k2 = false;
-#ifdef MMR_WITH_UMMA
-  k2 = uniform && umma_preferred(ix->dtype, ix->dim, B, k, int64_t(r1) - r0);
-#endif
-  if (uniform && !k2 && B <= (ix->dtype == MMR_F32 ? 8 : 4)) {
-    // K1 computes and pushes in ONE kernel: its last CTA stores the result into every peer over NVLink
-    int rc = search_uniform_stream(ix, queries_dev, B, k, r0, r1, w_scores, w_rows, ws, st, &xi);
+  const bool k2 = uniform && q.dev != nullptr && uniform_takes_k2(ix, B, k, int64_t(r1) - r0);
+  if (uniform && !k2 && B <= k1_group(ix) && (q.dev != nullptr || can_inline(ix, B))) {
+    // K1 computes and pushes in ONE kernel: its last CTA stores the result into the peers over NVLink
+    int rc = search_uniform_stream(ix, q, B, k, r0, r1, w_scores, w_rows, ws, st, &xi);
     if (rc != MMR_OK) return rc;
     pushed = true;
   } else {
-    int rc = mmr_search(ix, queries_dev, query_seg_host, B, k, w_scores, w_rows, ws, base_ws, st);
+    if (q.dev == nullptr) return fail(MMR_ERR_INVALID, "this batch needs device-resident queries");
+    int rc = uniform ? search_uniform(ix, q, B, k, r0, r1, w_scores, w_rows, ws, base_ws, st)
+                     : search_varlen_stream(ix, q.dev, *per_query, k, w_scores, w_rows, ws, base_ws, st);
     if (rc != MMR_OK) return rc;
   }
   // 2. push (when the scan kernel did not do it itself)
-  if (!pushed) {
+  if (!pushed && xi.n_peers > 0) {
     PeerPtrs pp;
     for (int g = 0; g < MMR_XCHG_MAX_PEERS; ++g) {
-      pp.slot[g] = g < G ? xi.slot[g] : 0;
-      pp.flag[g] = g < G ? xi.flag[g] : 0;
+      pp.slot[g] = g < xi.n_peers ? xi.slot[g] : 0;
+      pp.flag[g] = g < xi.n_peers ? xi.flag[g] : 0;
     }
-    push_wire_kernel<<<G, 256, 0, st>>>(wire, wire_bytes, pp, seq);
+    push_wire_kernel<<<xi.n_peers, 256, 0, st>>>(wire, wire_bytes, pp, seq);
     g_launches++;
   }
+  if (!do_merge) return MMR_OK;
   // 3. wait for every peer's slot, merge in place
-  const uint8_t* local = reinterpret_cast<const uint8_t*>(peer_bufs_host[rank]);
+  const uint8_t* local = reinterpret_cast<const uint8_t*>(peer_bufs[rank]);
   const int wpb = 4;
   const uint64_t timeout_ns = 5000000000ull;
   // With MMR_PDL=1 the wait+merge kernel is a programmatic dependent of the scan: it may become resident while the scan
   // still runs (it only spins on the flags, which the scan's last CTA releases at its very end) and the next search's
   // scan may in turn start behind it.  Otherwise plain stream order.
-  const char* pdl = getenv("MMR_PDL");
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((B + wpb - 1) / wpb);
   cfg.blockDim = dim3(wpb * 32);
@@ -730,16 +930,359 @@ extern "C" int mmr_search_exchange(const mmr_index* ix, const float* queries_dev
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = (pushed && pdl && pdl[0] == '1') ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = (pushed && options().pdl) ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  uint32_t* done_flag = nullptr;
+  uint32_t done_seq = 0;
+  if (done && done->flag_dev && cfg.gridDim.x == 1) {  // one block writes every result: it can ring the mailbox itself
+    done_flag = done->flag_dev;
+    done_seq = done->seq;
+    done->armed = true;
+  }
   if (k <= 32)
     CUDA_TRY(cudaLaunchKernelEx(&cfg, merge_wait_kernel<1>, local, parity, seq, wire_bytes, score_bytes, int(G), int(B),
-                                int(k), out_scores_dev, out_rows_dev, timeout_ns));
+                                int(k), out_s, out_r, timeout_ns, done_flag, done_seq));
   else
     CUDA_TRY(cudaLaunchKernelEx(&cfg, merge_wait_kernel<2>, local, parity, seq, wire_bytes, score_bytes, int(G), int(B),
-                                int(k), out_scores_dev, out_rows_dev, timeout_ns));
+                                int(k), out_s, out_r, timeout_ns, done_flag, done_seq));
   g_launches++;
+  return MMR_OK;
+}
+
+static int check_exchange_args(const mmr_index* ix, int B, int k, const uint64_t* peer_bufs_host, int G, int rank, uint32_t seq) {
+  int rc = check_search_args(ix, B, k);
+  if (rc != MMR_OK) return rc;
+  if (!peer_bufs_host || G < 1 || G > MMR_XCHG_MAX_PEERS || rank < 0 || rank >= G)
+    return fail(MMR_ERR_INVALID, "bad peer table (G=%d, rank=%d)", G, rank);
+  if (seq == 0) return fail(MMR_ERR_INVALID, "seq must start at 1 and grow by 1 per search");
+  return MMR_OK;
+}
+
+extern "C" int mmr_search_exchange(const mmr_index* ix, const float* queries_dev, const int32_t* query_seg_host,
+                                   int32_t B, int32_t k, const uint64_t* peer_bufs_host, int32_t G, int32_t rank,
+                                   uint32_t seq, float* out_scores_dev, int64_t* out_rows_dev, void* workspace_dev,
+                                   size_t workspace_bytes, void* stream) {
+  int rc = check_exchange_args(ix, B, k, peer_bufs_host, G, rank, seq);
+  if (rc != MMR_OK) return rc;
+  if (!queries_dev || !out_scores_dev || !out_rows_dev || !workspace_dev) return fail(MMR_ERR_INVALID, "NULL buffer");
+  const size_t base_ws = mmr_search_workspace_bytes(ix, B, k);
+  if (workspace_bytes < mmr_search_exchange_workspace_bytes(ix, B, k)) return fail(MMR_ERR_WORKSPACE, "workspace too small");
+  std::vector<RangeList> ranges;
+  bool uniform = true;
+  rc = ranges_from_segments(ix, query_seg_host, B, ranges, uniform);
+  if (rc != MMR_OK) return rc;
+  QuerySrc q;
+  q.dev = queries_dev;
+  return exchange_impl(ix, q, B, k, uniform, ranges[0][0].first, ranges[0][0].second, &ranges, peer_bufs_host, G, rank, seq,
+                       (G >= 32 ? 0xFFFFFFFFu : ((1u << G) - 1u)), true, out_scores_dev, out_rows_dev,
+                       static_cast<uint8_t*>(workspace_dev), base_ws, static_cast<cudaStream_t>(stream), nullptr);
+}
+
+// The same exchange with HOST buffers (one process per GPU, e.g. under torchrun): for B <= 2 the query rides in the scan
+// kernel's parameters, the wait+merge kernel writes the merged result and a completion flag into this index's mapped
+// mailbox, and the host spins on the flag -- no copies, no stream synchronisation on the request path.
+extern "C" int mmr_search_exchange_host(mmr_index* ix, const float* queries_host, const int32_t* query_seg_host, int32_t B,
+                                        int32_t k, const uint64_t* peer_bufs_host, int32_t G, int32_t rank, uint32_t seq,
+                                        float* out_scores_host, int64_t* out_rows_host, void* stream) {
+  int rc = check_exchange_args(ix, B, k, peer_bufs_host, G, rank, seq);
+  if (rc != MMR_OK) return rc;
+  if (!queries_host || !out_scores_host || !out_rows_host) return fail(MMR_ERR_INVALID, "NULL buffer");
+  std::lock_guard<std::mutex> guard(ix->host_mu);
+  CUDA_TRY(cudaSetDevice(ix->device));
+  rc = ensure_staging(ix, B, k);
+  if (rc != MMR_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::vector<RangeList> ranges;
+  bool uniform = true;
+  rc = ranges_from_segments(ix, query_seg_host, B, ranges, uniform);
+  if (rc != MMR_OK) return rc;
+  // the exchange wire sits behind the search workspace: the staging workspace must hold both
+  const size_t base_ws = workspace_bytes_for(ix, ix->cap_b, ix->cap_k, int64_t(RANGES_PER_QUERY_BUDGET) * ix->cap_b);
+  const size_t need = base_ws + align_up(xchg_wire_bytes(ix->cap_b, ix->cap_k), 256);
+  if (ix->ws_bytes < need) {
+    if (ix->d_ws) cudaFree(ix->d_ws);
+    ix->d_ws = nullptr;
+    CUDA_TRY(cudaMalloc(&ix->d_ws, need));
+    CUDA_TRY(cudaMemset(ix->d_ws, 0, need));
+    ix->ws_bytes = need;
+  }
+  float* box_s = reinterpret_cast<float*>(ix->d_box + BOX_HEADER);
+  int64_t* box_r = reinterpret_cast<int64_t*>(ix->d_box + box_rows_off(B, k));
+  Completion done;
+  done.flag_dev = reinterpret_cast<uint32_t*>(ix->d_box);
+  done.seq = ++ix->box_seq ? ix->box_seq : ++ix->box_seq;
+  QuerySrc q;
+  const uint32_t r0 = ranges[0][0].first, r1 = ranges[0][0].second;
+  if (uniform && can_inline(ix, B) && !uniform_takes_k2(ix, B, k, int64_t(r1) - r0)) {
+    q.host = queries_host;
+  } else {
+    memcpy(ix->h_q, queries_host, size_t(B) * ix->dim * 4);
+    CUDA_TRY(cudaMemcpyAsync(ix->d_q, ix->h_q, size_t(B) * ix->dim * 4, cudaMemcpyHostToDevice, st));
+    q.dev = ix->d_q;
+  }
+  rc = exchange_impl(ix, q, B, k, uniform, r0, r1, &ranges, peer_bufs_host, G, rank, seq,
+                     (G >= 32 ? 0xFFFFFFFFu : ((1u << G) - 1u)), true, box_s, box_r, static_cast<uint8_t*>(ix->d_ws),
+                     base_ws, st, &done);
+  if (rc != MMR_OK) return rc;
+  return finish_host_call(ix, done, B, k, out_scores_host, out_rows_host, st);
+}
+
+// ------------------------------------------------------------------------------------------------ one process, G GPUs
+// The reference has ONE store object in ONE process (app/ml/retrieve.py:21).  mmr_multi keeps that shape on a multi-GPU
+// box: G row-range shards (one mmr_index per device, row_base = first global row), one launcher thread and one stream
+// per device, and the same fused exchange as the SPMD form -- every shard's scan kernel stores its [B, k] result into the
+// COLLECTOR device's exchange buffer over NVLink peer mappings, and the collector's wait+merge kernel writes the final
+// result and a completion flag into a mapped host mailbox.  A request costs one kernel launch per device plus one merge
+// launch; no copies, no stream synchronisation.
+struct mmr_multi {
+  int G = 0;
+  std::vector<mmr_index*> shard;
+  std::vector<cudaStream_t> stream;
+  std::vector<uint8_t*> xbuf;
+  std::vector<uint64_t> peer_ptrs;
+  int cap_b = 0, cap_k = 0;
+  uint32_t seq = 0;       // exchange sequence number (restarts with the exchange buffers)
+  uint32_t mail_seq = 0;  // mailbox sequence number of the collector index (monotonic for the index's lifetime)
+  std::mutex call_mu;  // one search at a time
+  // job broadcast to the launcher threads
+  std::vector<std::thread> workers;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::atomic<uint64_t> job_seq{0};
+  std::atomic<int> pending{0};
+  std::atomic<bool> stop{false};
+  const float* q_host = nullptr;
+  const std::vector<RangeList>* ranges = nullptr;  // global row ranges per query
+  int B = 0, k = 0;
+  std::vector<int> rc;
+  std::vector<std::string> err;
+};
+
+static void multi_free_xbuf(mmr_multi* m) {
+  for (int g = 0; g < m->G; ++g) {
+    if (m->xbuf[g]) {
+      cudaSetDevice(m->shard[g]->device);
+      cudaFree(m->xbuf[g]);
+      m->xbuf[g] = nullptr;
+    }
+  }
+}
+
+// runs on launcher thread g with device g current
+static int multi_run_shard(mmr_multi* m, int g) {
+  mmr_index* ix = m->shard[g];
+  const int B = m->B, k = m->k;
+  std::lock_guard<std::mutex> guard(ix->host_mu);
+  int rc = ensure_staging(ix, std::max(B, m->cap_b), std::max(k, m->cap_k));
+  if (rc != MMR_OK) return rc;
+  const size_t base_ws = workspace_bytes_for(ix, ix->cap_b, ix->cap_k, int64_t(RANGES_PER_QUERY_BUDGET) * ix->cap_b);
+  const size_t need = base_ws + align_up(xchg_wire_bytes(ix->cap_b, ix->cap_k), 256);
+  if (ix->ws_bytes < need) {
+    if (ix->d_ws) cudaFree(ix->d_ws);
+    ix->d_ws = nullptr;
+    CUDA_TRY(cudaMalloc(&ix->d_ws, need));
+    CUDA_TRY(cudaMemset(ix->d_ws, 0, need));
+    ix->ws_bytes = need;
+  }
+  // clip the global ranges to this shard
+  const int64_t lo_g = ix->row_base, hi_g = ix->row_base + ix->n_rows;
+  std::vector<RangeList> local(B);
+  bool uniform = true;
+  for (int b = 0; b < B; ++b) {
+    for (auto& r : (*m->ranges)[b]) {
+      const int64_t lo = std::max<int64_t>(r.first, lo_g), hi = std::min<int64_t>(r.second, hi_g);
+      if (hi > lo) local[b].push_back({uint32_t(lo - lo_g), uint32_t(hi - lo_g)});
+    }
+    if (local[b].size() > 1 || local[b] != local[0]) uniform = false;
+  }
+  const uint32_t r0 = (uniform && !local[0].empty()) ? local[0][0].first : 0u;
+  const uint32_t r1 = (uniform && !local[0].empty()) ? local[0][0].second : 0u;
+  cudaStream_t st = m->stream[g];
+  QuerySrc q;
+  if (uniform && can_inline(ix, B) && !uniform_takes_k2(ix, B, k, int64_t(r1) - r0)) {
+    q.host = m->q_host;
+  } else {
+    memcpy(ix->h_q, m->q_host, size_t(B) * ix->dim * 4);
+    CUDA_TRY(cudaMemcpyAsync(ix->d_q, ix->h_q, size_t(B) * ix->dim * 4, cudaMemcpyHostToDevice, st));
+    q.dev = ix->d_q;
+  }
+  Completion done;
+  float* box_s = nullptr;
+  int64_t* box_r = nullptr;
+  if (g == 0) {  // the collector merges into its mailbox
+    box_s = reinterpret_cast<float*>(ix->d_box + BOX_HEADER);
+    box_r = reinterpret_cast<int64_t*>(ix->d_box + box_rows_off(B, k));
+    done.flag_dev = reinterpret_cast<uint32_t*>(ix->d_box);
+    done.seq = m->mail_seq;
+  }
+  rc = exchange_impl(ix, q, B, k, uniform, r0, r1, &local, m->peer_ptrs.data(), m->G, g, m->seq, 1u /* push to the collector */,
+                     g == 0, box_s, box_r, static_cast<uint8_t*>(ix->d_ws), base_ws, st, g == 0 ? &done : nullptr);
+  if (rc == MMR_OK && g == 0 && !done.armed) {
+    // multi-block merge (B > 4): no flag from the kernel; ring the mailbox when the stream drains
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *reinterpret_cast<volatile uint32_t*>(ix->h_box) = m->mail_seq;
+  }
+  return rc;
+}
+
+static void multi_worker(mmr_multi* m, int g) {
+  cudaSetDevice(m->shard[g]->device);
+  uint64_t seen = 0;
+  for (;;) {
+    // spin briefly (back-to-back requests find the launcher hot), then sleep on the condition variable
+    int spins = 0;
+    while (m->job_seq.load(std::memory_order_acquire) == seen && !m->stop.load(std::memory_order_relaxed)) {
+      if (++spins < 20000) {
+        cpu_relax();
+      } else {
+        std::unique_lock<std::mutex> lk(m->mu);
+        m->cv.wait_for(lk, std::chrono::milliseconds(50), [&] {
+          return m->job_seq.load(std::memory_order_acquire) != seen || m->stop.load(std::memory_order_relaxed);
+        });
+      }
+    }
+    if (m->stop.load(std::memory_order_relaxed)) return;
+    seen = m->job_seq.load(std::memory_order_acquire);
+    m->rc[g] = multi_run_shard(m, g);
+    if (m->rc[g] != MMR_OK) m->err[g] = g_err;
+    m->pending.fetch_sub(1, std::memory_order_acq_rel);
+  }
+}
+
+extern "C" int mmr_multi_create(mmr_index** shards, int32_t G, mmr_multi** out) {
+  if (!out) return fail(MMR_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (!shards || G < 1 || G > MMR_XCHG_MAX_PEERS) return fail(MMR_ERR_INVALID, "need 1..%d shards", MMR_XCHG_MAX_PEERS);
+  for (int g = 0; g < G; ++g) {
+    if (!shards[g]) return fail(MMR_ERR_INVALID, "shard %d is NULL", g);
+    if (shards[g]->dim != shards[0]->dim || shards[g]->dtype != shards[0]->dtype)
+      return fail(MMR_ERR_INVALID, "shards must share dim and dtype");
+    for (int h = 0; h < g; ++h)
+      if (shards[h]->device == shards[g]->device) return fail(MMR_ERR_INVALID, "one shard per device");
+  }
+  mmr_multi* m = new mmr_multi();
+  m->G = G;
+  m->shard.assign(shards, shards + G);
+  m->stream.assign(G, nullptr);
+  m->xbuf.assign(G, nullptr);
+  m->peer_ptrs.assign(G, 0);
+  m->rc.assign(G, MMR_OK);
+  m->err.assign(G, std::string());
+  const int collector = shards[0]->device;
+  for (int g = 0; g < G; ++g) {
+    const int dev = shards[g]->device;
+    if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&m->stream[g], cudaStreamNonBlocking) != cudaSuccess) {
+      delete m;
+      return fail(MMR_ERR_CUDA, "cannot create a stream on device %d", dev);
+    }
+    if (dev != collector) {  // shard g's scan kernel stores into the collector's exchange buffer
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, dev, collector);
+      if (!can) {
+        delete m;
+        return fail(MMR_ERR_CUDA, "device %d cannot access device %d (no NVLink / P2P)", dev, collector);
+      }
+      cudaError_t e = cudaDeviceEnablePeerAccess(collector, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+        delete m;
+        return fail(MMR_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", dev, collector, cudaGetErrorString(e));
+      }
+      cudaGetLastError();
+    }
+  }
+  for (int g = 0; g < G; ++g) m->workers.emplace_back(multi_worker, m, g);
+  *out = m;
+  return MMR_OK;
+}
+
+extern "C" int mmr_multi_destroy(mmr_multi* m) {
+  if (!m) return MMR_OK;
+  m->stop.store(true);
+  {
+    std::lock_guard<std::mutex> lk(m->mu);
+    m->cv.notify_all();
+  }
+  for (auto& t : m->workers) t.join();
+  multi_free_xbuf(m);
+  for (int g = 0; g < m->G; ++g) {
+    if (m->stream[g]) {
+      cudaSetDevice(m->shard[g]->device);
+      cudaStreamDestroy(m->stream[g]);
+    }
+  }
+  delete m;
+  return MMR_OK;
+}
+
+extern "C" int mmr_multi_search_host(mmr_multi* m, const float* queries_host, int32_t B, int32_t k,
+                                     const int32_t* range_off_host, const int64_t* ranges_host, float* out_scores_host,
+                                     int64_t* out_rows_host) {
+  if (!m) return fail(MMR_ERR_INVALID, "multi handle is NULL");
+  int rc = check_search_args(m->shard[0], B, k);
+  if (rc != MMR_OK) return rc;
+  if (!queries_host || !range_off_host || !out_scores_host || !out_rows_host) return fail(MMR_ERR_INVALID, "NULL buffer");
+  std::lock_guard<std::mutex> call_guard(m->call_mu);
+  // global ranges (validated against the global row count)
+  int64_t total = 0;
+  for (int g = 0; g < m->G; ++g) total = std::max<int64_t>(total, m->shard[g]->row_base + m->shard[g]->n_rows);
+  std::vector<RangeList> per_query(B);
+  for (int b = 0; b < B; ++b) {
+    if (range_off_host[b + 1] < range_off_host[b]) return fail(MMR_ERR_INVALID, "range offsets must be ascending");
+    for (int32_t r = range_off_host[b]; r < range_off_host[b + 1]; ++r) {
+      const int64_t lo = ranges_host[2 * r], hi = ranges_host[2 * r + 1];
+      if (lo < 0 || hi < lo || hi > total || hi >= (int64_t(1) << 32))
+        return fail(MMR_ERR_INVALID, "query %d: bad row range [%lld, %lld)", b, (long long)lo, (long long)hi);
+      if (hi > lo) per_query[b].push_back({uint32_t(lo), uint32_t(hi)});
+    }
+    RangeList sorted = per_query[b];
+    std::sort(sorted.begin(), sorted.end());
+    for (size_t i = 1; i < sorted.size(); ++i)
+      if (sorted[i].first < sorted[i - 1].second) return fail(MMR_ERR_INVALID, "query %d: row ranges overlap", b);
+  }
+  // (re)size the exchange buffers: zeroed once, sequence numbers restart with them
+  if (B > m->cap_b || k > m->cap_k) {
+    for (int g = 0; g < m->G; ++g) CUDA_TRY((cudaSetDevice(m->shard[g]->device), cudaStreamSynchronize(m->stream[g])));
+    multi_free_xbuf(m);
+    const int cb = std::max(B, 8), ck = std::max(k, 16);
+    const size_t bytes = mmr_exchange_buffer_bytes(m->G, cb, ck);
+    for (int g = 0; g < m->G; ++g) {
+      CUDA_TRY(cudaSetDevice(m->shard[g]->device));
+      CUDA_TRY(cudaMalloc(&m->xbuf[g], bytes));
+      CUDA_TRY(cudaMemset(m->xbuf[g], 0, bytes));
+      CUDA_TRY(cudaDeviceSynchronize());
+      m->peer_ptrs[g] = reinterpret_cast<uint64_t>(m->xbuf[g]);
+    }
+    m->cap_b = cb;
+    m->cap_k = ck;
+    m->seq = 0;
+  }
+  // NOTE the wire layout depends on (B, k): slots of different shapes never mix inside one sequence number
+  m->seq += 1;
+  {
+    std::lock_guard<std::mutex> box_guard(m->shard[0]->host_mu);
+    m->mail_seq = ++m->shard[0]->box_seq ? m->shard[0]->box_seq : ++m->shard[0]->box_seq;
+  }
+  m->q_host = queries_host;
+  m->ranges = &per_query;
+  m->B = B;
+  m->k = k;
+  m->pending.store(m->G, std::memory_order_release);
+  {
+    std::lock_guard<std::mutex> lk(m->mu);
+    m->job_seq.fetch_add(1, std::memory_order_acq_rel);
+  }
+  m->cv.notify_all();
+  while (m->pending.load(std::memory_order_acquire) != 0) cpu_relax();   // every launcher has issued its work
+  for (int g = 0; g < m->G; ++g)
+    if (m->rc[g] != MMR_OK) return fail(m->rc[g], "shard %d: %s", g, m->err[g].c_str());
+  mmr_index* c = m->shard[0];
+  CUDA_TRY(cudaSetDevice(c->device));
+  rc = wait_mailbox(c, m->mail_seq, m->stream[0]);
+  if (rc != MMR_OK) return rc;
+  memcpy(out_scores_host, c->h_box + BOX_HEADER, size_t(B) * k * 4);
+  memcpy(out_rows_host, c->h_box + box_rows_off(B, k), size_t(B) * k * 8);
+  if (out_rows_host[0] == -2) return fail(MMR_ERR_CUDA, "exchange timed out: a shard never delivered its result");
   return MMR_OK;
 }
 

@@ -41,23 +41,35 @@ constexpr int K1_NW = MMR_K1_NW;   // consumer warps per CTA
 constexpr int K1_THREADS = K1_NW * 32;
 constexpr int MMR_MAX_PEERS = 16;
 
-struct ScanItem {  // varlen mode: one contiguous row range of one query (rows are index-local ordinals)
+constexpr int K1_ITEM_NQ = 4;        // queries per varlen work item (one pass over the item's rows serves all of them)
+constexpr int K1_INLINE_FLOATS = 1024;  // queries that ride in the kernel parameters (2 x 512 floats)
+
+struct ScanItem {  // varlen mode: one contiguous row range scanned for up to K1_ITEM_NQ queries that share it
   uint32_t row_begin;
   uint32_t row_end;
-  int32_t query;
+  int32_t query[K1_ITEM_NQ];  // query ordinals; entries >= nq are ignored
+  int32_t nq;
+  int32_t pad;
+};
+
+struct QuerySlot {  // varlen mode: where query b's partial lists are: items [item0, item0 + n_items), list `slot` of each
+  int32_t item0;
+  int32_t n_items;
+  int32_t slot;
   int32_t pad;
 };
 
 struct StreamParams {
   const void* rows;      // [n_rows, D] row-major, elem type E
-  const float* queries;  // [B, D] fp32, not necessarily unit norm (re-normalised here, lancedb_store.py:104)
+  const float* queries;  // [B, D] fp32, not necessarily unit norm (re-normalised here, lancedb_store.py:104);
+                         // nullptr = the queries are in `qinline` (host-buffer calls: no H2D copy at all)
   int32_t q_first;       // first query of this group
   int32_t nq;            // live queries in this group (1..NQ)
   int32_t k;
   uint32_t row_begin, row_end;  // uniform mode: the shared row range
-  uint64_t* partial;            // uniform: [grid, NQ, k]; varlen: [n_items, k]
+  uint64_t* partial;            // uniform: [grid, NQ, k]; varlen: [n_items, NQ, k]
   unsigned int* ticket;         // zero on entry, left zero on exit
-  float* out_scores;            // [B, k]  (uniform mode only)
+  float* out_scores;            // [B, k]  (uniform mode only; may be mapped host memory)
   int64_t* out_rows;            // [B, k]
   int64_t row_base;             // shard base added to the int64 row ids written out
   const ScanItem* items;        // varlen mode (nullptr = uniform)
@@ -69,6 +81,11 @@ struct StreamParams {
   uint32_t wire_score_bytes;    // offset of the int64 rows inside one wire slot
   uint64_t peer_slot[MMR_MAX_PEERS];  // address of this rank's slot inside peer g's buffer (peer-mapped)
   uint64_t peer_flag[MMR_MAX_PEERS];  // address of this rank's flag inside peer g's buffer
+  // Completion mailbox (host-buffer calls): after the results are written, done_flag (mapped host memory) is released
+  // with done_seq at system scope, so the host can spin on it instead of synchronising the stream.
+  uint32_t* done_flag;
+  uint32_t done_seq;
+  float qinline[K1_INLINE_FLOATS];
 };
 
 template <typename E>
@@ -149,7 +166,7 @@ struct StreamCfg {
 };
 
 template <typename E, int D, int NQ, int KPL>
-__global__ void __launch_bounds__(K1_THREADS, 1) scan_stream_kernel(const StreamParams p) {
+__global__ void __launch_bounds__(K1_THREADS, 1) scan_stream_kernel(const __grid_constant__ StreamParams p) {
   using C = StreamCfg<E, D, NQ, KPL>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::RING_BYTES);
@@ -179,7 +196,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) scan_stream_kernel(const Stream
 #pragma unroll
   for (int qi = 0; qi < NQ; ++qi) {
     const bool live = qi < p.nq;
-    const float* qsrc = p.queries + size_t(p.items ? 0 : (p.q_first + (live ? qi : 0))) * D;
+    const float* qbase = p.queries ? p.queries : p.qinline;
+    const float* qsrc = qbase + size_t(p.items ? 0 : (p.q_first + (live ? qi : 0))) * D;
     float ss = 0.f;
 #pragma unroll
     for (int t = 0; t < C::NV; ++t)
@@ -212,6 +230,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) scan_stream_kernel(const Stream
 
   int stage = 0;          // next ring stage this warp consumes (persists across row ranges)
   uint32_t phase = 0;     // mbarrier parity of that stage
+  int nq_live = p.nq;     // live queries of the current job (varlen: per item)
 
   // One "job" = a row range scanned with chunk index c = first, first+stride, ...
   auto scan_range = [&](uint32_t row_begin, uint32_t row_end, int first, int stride) {
@@ -295,7 +314,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) scan_stream_kernel(const Stream
       const uint64_t key = make_key(score, row);
 #pragma unroll
       for (int qi = 0; qi < NQ; ++qi) {
-        if (qi < p.nq) thr[qi] = list[qi].offer(key, owner && myq == qi, thr[qi], k, lane);
+        if (qi < nq_live) thr[qi] = list[qi].offer(key, owner && myq == qi, thr[qi], k, lane);
       }
       if (++stage == C::S) {
         stage = 0;
@@ -387,57 +406,74 @@ __global__ void __launch_bounds__(K1_THREADS, 1) scan_stream_kernel(const Stream
     }
     if (threadIdx.x == 0) *p.ticket = 0u;  // ready for the next launch (before the flags: a pipelined successor
                                            // may pass its dependency wait as soon as the exchange completes)
-    if (p.n_peers > 0) {
+    if (p.n_peers > 0 || p.done_flag != nullptr) {
       __threadfence_system();
       __syncthreads();
       if (int(threadIdx.x) < p.n_peers)
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.peer_flag[threadIdx.x]), "r"(p.seq) : "memory");
+      if (threadIdx.x == 0 && p.done_flag != nullptr)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.done_flag), "r"(p.done_seq) : "memory");
     }
   } else {
-    // ------------------------------ varlen mode (NQ == 1) ------------------------------
-    // item i -> global warp (i mod total_warps); each item is one (query, row range); the partial of
-    // every item is merged per query by merge_items_kernel.
+    // ------------------------------ varlen mode ------------------------------
+    // item i -> global warp (i mod total_warps); each item is one row range scanned for up to NQ queries that share
+    // it (the queries of one tenant in this batch, grouped by the host planner: the rows are read once for the group);
+    // the partial lists of every item are merged per query by merge_items_kernel.
     for (int it = gwarp; it < p.n_items; it += twarps) {
       const ScanItem item = p.items[it];
-      // load + normalise this item's query
-      const float* qsrc = p.queries + size_t(item.query) * D;
-      float ss = 0.f;
+      nq_live = min(item.nq, NQ);
 #pragma unroll
-      for (int t = 0; t < C::NV; ++t)
+      for (int qi = 0; qi < NQ; ++qi) {
+        // load + normalise this item's queries (dead slots read query 0 of the item and are never offered)
+        const float* qsrc = p.queries + size_t(item.query[qi < nq_live ? qi : 0]) * D;
+        float ss = 0.f;
 #pragma unroll
-        for (int j = 0; j < C::RPV * C::EPR; ++j) {
-          const float x = qsrc[(t * 32 + lane) * (C::RPV * C::EPR) + j];
-          q[0][t * C::RPV * C::EPR + j] = x;
-          ss += x * x;
+        for (int t = 0; t < C::NV; ++t)
+#pragma unroll
+          for (int j = 0; j < C::RPV * C::EPR; ++j) {
+            const float x = qsrc[(t * 32 + lane) * (C::RPV * C::EPR) + j];
+            q[qi][t * C::RPV * C::EPR + j] = x;
+            ss += x * x;
+          }
+        ss = warp_allreduce_sum(ss);
+        const float nrm = sqrtf(ss);
+        if (nrm > 0.f) {
+#pragma unroll
+          for (int e = 0; e < C::EPL; ++e) q[qi][e] = q[qi][e] / nrm;
         }
-      ss = warp_allreduce_sum(ss);
-      const float nrm = sqrtf(ss);
-      if (nrm > 0.f) {
-#pragma unroll
-        for (int e = 0; e < C::EPL; ++e) q[0][e] = q[0][e] / nrm;
+        list[qi].clear();
+        thr[qi] = 0ull;
       }
-      list[0].clear();
-      thr[0] = 0ull;
       scan_range(item.row_begin, item.row_end, 0, 1);
-      list[0].store(p.partial + size_t(it) * k, k, lane);
+#pragma unroll
+      for (int qi = 0; qi < NQ; ++qi)
+        if (qi < nq_live) list[qi].store(p.partial + (size_t(it) * NQ + qi) * k, k, lane);
     }
   }
 }
 
-// Varlen tail: one warp per query merges the partial lists of that query's items
-// (items of a query are contiguous: [item_off[q], item_off[q+1])).
+// Varlen tail: one warp per query merges the partial lists of that query (list `slot` of the items
+// [item0, item0 + n_items) of its group; partial is [n_items_total][nq_per_item][k]).
 template <int KPL>
-__global__ void merge_items_kernel(const uint64_t* __restrict__ partial, const int32_t* __restrict__ item_off, int nq,
-                                   int k, float* __restrict__ out_scores, int64_t* __restrict__ out_rows,
-                                   int64_t row_base) {
+__global__ void merge_items_kernel(const uint64_t* __restrict__ partial, const QuerySlot* __restrict__ slots, int nq,
+                                   int nq_per_item, int k, float* __restrict__ out_scores,
+                                   int64_t* __restrict__ out_rows, int64_t row_base) {
   const int lane = threadIdx.x & 31;
   const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (qi >= nq) return;
   WarpTopK<KPL> m;
   m.clear();
   uint64_t t = 0ull;
-  const int i0 = item_off[qi], i1 = item_off[qi + 1];
-  t = m.template merge_from<true>(partial + size_t(i0) * k, (i1 - i0) * k, 1, t, k, lane);
+  const QuerySlot sl = slots[qi];
+  const uint64_t* base = partial + (size_t(sl.item0) * nq_per_item + sl.slot) * k;
+  const size_t item_stride = size_t(nq_per_item) * k;
+  // position-major over the items' lists (all heads first), 4 loads in flight per lane
+  t = m.template merge_batched<4>(
+      [&](int i) -> uint64_t {
+        const int item = i % sl.n_items, pos = i / sl.n_items;
+        return __ldcg(reinterpret_cast<const unsigned long long*>(base) + size_t(item) * item_stride + pos);
+      },
+      sl.n_items * k, t, k, lane);
 #pragma unroll
   for (int j = 0; j < KPL; ++j) {
     const int pos = j * 32 + lane;

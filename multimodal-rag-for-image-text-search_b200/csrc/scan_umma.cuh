@@ -352,7 +352,12 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     float thr_floor = -INFINITY;
     if (p.floor != nullptr && live) {
       const float f = p.floor[qglob];
-      if (f > -INFINITY) thr_floor = f32_from_orderable(f32_orderable(f) - 1u);
+      // the float just below f in the total order; below +-0 that is the largest negative subnormal, not -0.0
+      // (which compares equal to 0 and would reject every row scoring exactly 0, e.g. for an all-zero query)
+      if (f > -INFINITY) {
+        const uint32_t o = f32_orderable(f);
+        thr_floor = f32_from_orderable(o - (o == 0x80000000u ? 2u : 1u));
+      }
     }
     float thr_f = live ? thr_floor : INFINITY;
     float best = -INFINITY;  // probe pass
@@ -514,6 +519,11 @@ struct UmmaIndexState {
   const void* rows = nullptr;
   int64_t n_rows = 0;
   CUtensorMap map;
+  // the query tile's map is cached too: a search re-encodes it only when the query copy moved or its shape changed
+  bool q_valid = false;
+  const void* q_ptr = nullptr;
+  int q_rows = 0;
+  CUtensorMap q_map;
 };
 
 typedef CUresult (*mmr_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -576,9 +586,9 @@ inline int umma_plan_stages(int dim, int k, size_t* smem_bytes, bool ts = false)
 //   B <= 2  : K1 (fp32 queries, one launch, HBM-bound)      B >= 3, bf16/fp16 rows : K2 (16-bit queries on tcgen05)
 inline bool umma_preferred(int dtype, int dim, int B, int k, int64_t nrows) {
   // MMR_FORCE_FAMILY=1|2 (measurement only, profiles/r01_k2_summary.md "crossover"): pin the family regardless of B
-  const char* force = getenv("MMR_FORCE_FAMILY");
-  const int min_b = (force && force[0] == '2') ? 1 : 3;
-  if (force && force[0] == '1') return false;
+  const int force = options().force_family;
+  const int min_b = force == 2 ? 1 : 3;
+  if (force == 1) return false;
   if ((dtype != MMR_BF16 && dtype != MMR_F16) || dim % 64 != 0 || B < min_b) return false;
   if (nrows <= 0 || nrows >= (int64_t(1) << 31)) return false;
   return umma_plan_stages(dim, k, nullptr) >= 2;

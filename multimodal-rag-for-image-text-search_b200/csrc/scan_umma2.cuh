@@ -228,7 +228,12 @@ scan_umma2_kernel(const __grid_constant__ CUtensorMap tm_x, const UmmaParams p) 
     float thr_floor = -INFINITY;
     if (p.floor != nullptr && live) {
       const float f = p.floor[qglob];
-      if (f > -INFINITY) thr_floor = f32_from_orderable(f32_orderable(f) - 1u);
+      // the float just below f in the total order; below +-0 that is the largest negative subnormal, not -0.0
+      // (which compares equal to 0 and would reject every row scoring exactly 0, e.g. for an all-zero query)
+      if (f > -INFINITY) {
+        const uint32_t o = f32_orderable(f);
+        thr_floor = f32_from_orderable(o - (o == 0x80000000u ? 2u : 1u));
+      }
     }
     float thr_f = live ? thr_floor : INFINITY;
     float best = -INFINITY;
@@ -360,10 +365,9 @@ inline int umma_search(UmmaIndexState& st, Umma2IndexState& st2, const void* row
   // HBM-bound and fastest with both operands in shared memory and 4 accumulators; several query tiles are
   // tensor-bound and fastest with the query tile in tensor memory (half the shared-memory reads per MMA, 13-deep
   // ring).  MMR_UMMA_MODE=ss|ts overrides.
-  const char* mode = getenv("MMR_UMMA_MODE");
   bool ts = umma_qtiles(B) > 1;
-  if (mode && mode[0] == 's') ts = false;
-  if (mode && mode[0] == 't') ts = true;
+  if (options().umma_mode == 1) ts = false;
+  if (options().umma_mode == 2) ts = true;
   if (dim / 2 + 2 * K2_NT > 512) ts = false;
   size_t smem_bytes = 0;
   const int stages = umma_plan_stages(dim, k, &smem_bytes, ts);
@@ -386,8 +390,7 @@ inline int umma_search(UmmaIndexState& st, Umma2IndexState& st2, const void* row
   }
   // CTA pairs (cta_group::2) for the tensor-bound regime (at least two query tiles): 5-9 % faster than cta_group::1
   // there (B=1024: 8.30 vs 8.72 ms, profiles/r01_k2_summary.md).  MMR_UMMA_PAIR=0 falls back to single CTAs.
-  const char* pair_env = getenv("MMR_UMMA_PAIR");
-  bool pair = ts && umma_qtiles(B) >= 2 && !(pair_env && pair_env[0] == '0');
+  bool pair = ts && umma_qtiles(B) >= 2 && options().umma_pair != 0;
   size_t smem2_bytes = 0;
   const int stages2 = umma2_plan_stages(k, &smem2_bytes);
   if (stages2 < 4) pair = false;
@@ -405,17 +408,27 @@ inline int umma_search(UmmaIndexState& st, Umma2IndexState& st2, const void* row
   const int ctas_max = std::max(sm_count, std::min(umma_qtiles(B), sm_count));
   float* probe = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(partial) + umma_align(size_t(ctas_max) * K2_BM * k * 8));
   float* floor = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(probe) + umma_align(size_t(ctas_max) * K2_BM * 4));
-  const char* noprobe = getenv("MMR_UMMA_NOPROBE");
+  const bool noprobe = options().umma_noprobe != 0;
   if (dtype == MMR_BF16) launch_pdl(prep_queries_kernel<__nv_bfloat16>, dim3((B + 3) / 4), dim3(128), 0, stream, queries, qb, B, dim);
   else launch_pdl(prep_queries_kernel<__half>, dim3((B + 3) / 4), dim3(128), 0, stream, queries, reinterpret_cast<__half*>(qb), B, dim);
   const int max_q_per_pass = sm_count * K2_BM;
   for (int q0 = 0; q0 < B; q0 += max_q_per_pass) {
     const int bq = std::min(B - q0, max_q_per_pass);
-    CUtensorMap tm_q;
-    if (!umma_make_map(&tm_q, qb + size_t(q0) * dim, bq, dim, dtype == MMR_BF16)) {
-      err = "cuTensorMapEncodeTiled failed for the queries";
-      return MMR_ERR_CUDA;
+    CUtensorMap tm_q_local;
+    const void* qptr = qb + size_t(q0) * dim;
+    const bool cacheable = (q0 == 0);
+    if (!(cacheable && st.q_valid && st.q_ptr == qptr && st.q_rows == bq)) {
+      if (!umma_make_map(cacheable ? &st.q_map : &tm_q_local, qptr, bq, dim, dtype == MMR_BF16)) {
+        err = "cuTensorMapEncodeTiled failed for the queries";
+        return MMR_ERR_CUDA;
+      }
+      if (cacheable) {
+        st.q_valid = true;
+        st.q_ptr = qptr;
+        st.q_rows = bq;
+      }
     }
+    const CUtensorMap& tm_q = cacheable ? st.q_map : tm_q_local;
     UmmaParams p{};
     p.ks = dim / 64;
     p.idesc = umma_idesc_m128_n128(dtype == MMR_BF16);
@@ -441,7 +454,7 @@ inline int umma_search(UmmaIndexState& st, Umma2IndexState& st2, const void* row
     const int grid = pair ? 2 * n_qpairs * p.n_rslots : p.n_qtiles * p.n_rslots;
     // probe pass: worth it when every CTA streams many tiles (the warm-up it removes is ~k ln(n/k) inserts/thread)
     const int64_t tiles_per_cta = ntiles / p.n_rslots;
-    if (!dump && !(noprobe && noprobe[0] == '1') && tiles_per_cta >= 8 && p.n_rslots >= k) {
+    if (!dump && !noprobe && tiles_per_cta >= 8 && p.n_rslots >= k) {
       UmmaParams pp = p;
       pp.probe_out = probe;
       pp.probe_tiles = int(std::max<int64_t>(1, std::min<int64_t>(16, tiles_per_cta / 24)));

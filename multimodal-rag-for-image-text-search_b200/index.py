@@ -81,6 +81,42 @@ class ResidentIndex:
                                                  int(normalize), _stream_ptr(device)))
         return cls(dst, seg_offsets, row_base)
 
+    @staticmethod
+    def alloc_rows(n: int, dim: int, dtype: str, device) -> torch.Tensor:
+        """Uninitialised resident buffer [n, dim] of the storage type `dtype`."""
+        return torch.empty((int(n), int(dim)), dtype=_DTYPES[dtype][1], device=torch.device(device))
+
+    @staticmethod
+    def load_rows_into(buf: torch.Tensor, src_f32: np.ndarray, dst_rows: Optional[np.ndarray] = None,
+                       dst_offset: int = 0, normalize: bool = False) -> None:
+        """L1 loader into an existing resident buffer: host fp32 rows -> `buf`'s storage type.
+
+        dst_rows given : source row i lands in buf[dst_rows[i]] (negative = skip) -- a host block in insertion order goes
+                         straight to its tenant-sorted place, nothing is gathered on the host;
+        dst_rows None  : the rows land contiguously at buf[dst_offset : dst_offset + n].
+        Streams through pinned staging (mmr_load_rows_f32_host_scatter); returns when the rows are resident."""
+        kinds = {v[1]: v[0] for v in _DTYPES.values()}
+        src = np.ascontiguousarray(src_f32, dtype=np.float32)
+        n, d = src.shape
+        if n == 0:
+            return
+        if d != buf.shape[1]:
+            raise ValueError(f"row length {d} != resident row length {buf.shape[1]}")
+        dev = buf.device
+        esize = buf.element_size()
+        if dst_rows is not None:
+            m = np.ascontiguousarray(dst_rows, dtype=np.int64)
+            if m.shape != (n,) or (m.size and int(m.max()) >= buf.shape[0]):
+                raise ValueError("dst_rows must hold one in-range resident row per source row")
+            dst_ptr, mp = buf.data_ptr(), m.ctypes.data
+        else:
+            if dst_offset < 0 or dst_offset + n > buf.shape[0]:
+                raise ValueError("rows do not fit the resident buffer")
+            dst_ptr, mp = buf.data_ptr() + dst_offset * d * esize, None
+        with torch.cuda.device(dev):
+            N.check(N.lib().mmr_load_rows_f32_host_scatter(dev.index or 0, src.ctypes.data, dst_ptr, kinds[buf.dtype], n, d,
+                                                           int(normalize), mp, _stream_ptr(dev)))
+
     def update(self, rows: torch.Tensor, n_rows: Optional[int] = None, seg_offsets=None) -> None:
         """Re-point the handle at grown / rewritten rows (same dim and dtype) after an upsert; the first n_rows rows
         of `rows` are live (`rows` may be a larger capacity buffer)."""
@@ -107,7 +143,7 @@ class ResidentIndex:
         arr = np.ascontiguousarray(flat, dtype=np.int64).reshape(-1, 2) if flat else np.zeros((1, 2), np.int64)
         scores = torch.empty((b, k), dtype=torch.float32, device=self.device)
         rows = torch.empty((b, k), dtype=torch.int64, device=self.device)
-        ws = self._workspace(b, k)
+        ws = self._workspace(b, k, n_ranges=len(flat))
         with torch.cuda.device(self.device):
             N.check(N.lib().mmr_search_ranges(self._handle, queries.data_ptr(), b, k, off.ctypes.data, arr.ctypes.data,
                                               scores.data_ptr(), rows.data_ptr(), ws.data_ptr(), ws.numel(),
@@ -126,11 +162,18 @@ class ResidentIndex:
             pass
 
     # -- search ---------------------------------------------------------------------------------
-    def _workspace(self, b: int, k: int) -> torch.Tensor:
-        need = N.lib().mmr_search_workspace_bytes(self._handle, b, k)
+    def _workspace(self, b: int, k: int, n_ranges: int = 0) -> torch.Tensor:
+        lib = N.lib()
+        need = max(lib.mmr_search_workspace_bytes(self._handle, b, k),
+                   lib.mmr_search_ranges_workspace_bytes(self._handle, b, k, n_ranges) if n_ranges else 0)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.zeros(int(need), dtype=torch.uint8, device=self.device)
         return self._ws
+
+    def set_query_precision(self, mode: str) -> None:
+        """"auto": batches of >= 3 queries on one row range use the tensor-core kernels (16-bit queries);
+        "f32": every query is scored in fp32, so a request's result never depends on its batch (serving default)."""
+        N.check(N.lib().mmr_index_set_query_precision(self._handle, {"auto": N.MMR_QP_AUTO, "f32": N.MMR_QP_F32}[mode]))
 
     def search(self, queries: torch.Tensor, k: int, segments: Optional[Sequence[int]] = None,
                out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -186,6 +229,54 @@ class ResidentIndex:
             N.check(N.lib().mmr_search_host(self._handle, q.ctypes.data, None if seg_arr is None else seg_arr.ctypes.data,
                                             b, k, scores.ctypes.data, rows.ctypes.data, _stream_ptr(self.device)))
         return scores, rows
+
+
+class MultiIndex:
+    """G row-range shards of ONE table on the G GPUs of a box, searched from ONE process (mmr_multi_*): one scan launch
+    per device from per-device launcher threads, results pushed into the collector's buffer over NVLink peer mappings,
+    merged result + completion flag in a mapped host mailbox.  `shards[g]` must have row_base = its first global row."""
+
+    def __init__(self, shards: Sequence[ResidentIndex]) -> None:
+        self.shards = list(shards)
+        self._handle = C.c_void_p()
+        arr = (C.c_void_p * len(self.shards))(*[s._handle for s in self.shards])
+        N.check(N.lib().mmr_multi_create(arr, len(self.shards), C.byref(self._handle)))
+        self.dim = self.shards[0].dim
+        self.n_rows = max(s.row_base + s.n_rows for s in self.shards)
+
+    def search_host(self, queries: np.ndarray, k: int, ranges=None):
+        """queries [B, dim] f32 (host) -> numpy (scores [B,k], rows [B,k] global ids).  ranges[b] = [(lo, hi), ...]
+        global row ranges; None = the whole table for every query."""
+        q = np.ascontiguousarray(np.atleast_2d(queries), dtype=np.float32)
+        if q.shape[1] != self.dim:
+            raise ValueError(f"query dim {q.shape[1]} != index dim {self.dim}")
+        b = q.shape[0]
+        k = max(int(k), 1)
+        if ranges is None:
+            ranges = [[(0, self.n_rows)]] * b
+        off = np.zeros(b + 1, dtype=np.int32)
+        flat = []
+        for i, rq in enumerate(ranges):
+            flat.extend(rq)
+            off[i + 1] = len(flat)
+        arr = np.ascontiguousarray(flat, dtype=np.int64).reshape(-1, 2) if flat else np.zeros((1, 2), np.int64)
+        scores = np.empty((b, k), dtype=np.float32)
+        rows = np.empty((b, k), dtype=np.int64)
+        with torch.cuda.device(self.shards[0].device):   # the call leaves the collector's device current: restore ours
+            N.check(N.lib().mmr_multi_search_host(self._handle, q.ctypes.data, b, k, off.ctypes.data, arr.ctypes.data,
+                                                  scores.ctypes.data, rows.ctypes.data))
+        return scores, rows
+
+    def close(self) -> None:
+        if self._handle:
+            N.lib().mmr_multi_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def merge_topk(scores: torch.Tensor, rows: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -145,6 +145,30 @@ class ShardedIndex:
                                             _stream_ptr(ix.device)))
         return out
 
+    def search_host(self, queries: np.ndarray, k: int, segments=None) -> Tuple[np.ndarray, np.ndarray]:
+        """Host query in, host result out (identical on every rank) through mmr_search_exchange_host: for B <= 2 the query
+        rides in the scan kernel's parameters and the merged result lands in a mapped mailbox -- no copies, no stream
+        synchronisation.  Needs the fused exchange (symmetric memory)."""
+        from . import _native as N
+        from .index import _stream_ptr
+
+        q = np.ascontiguousarray(np.atleast_2d(queries), dtype=np.float32)
+        b, k = int(q.shape[0]), max(int(k), 1)
+        peer = self._peer_exchange(b, k)
+        if peer is None:
+            out = self.search(torch.from_numpy(q).to(self.local.device), k, segments)
+            return out[0].cpu().numpy(), out[1].cpu().numpy()
+        ix = self.local
+        scores = np.empty((b, k), dtype=np.float32)
+        rows = np.empty((b, k), dtype=np.int64)
+        seg_arr = None if segments is None else np.ascontiguousarray(segments, dtype=np.int32)
+        peer.seq += 1
+        with torch.cuda.device(ix.device):
+            N.check(N.lib().mmr_search_exchange_host(ix._handle, q.ctypes.data, None if seg_arr is None else seg_arr.ctypes.data,
+                                                     b, k, peer.ptrs.ctypes.data, self.world, self.rank, peer.seq,
+                                                     scores.ctypes.data, rows.ctypes.data, _stream_ptr(ix.device)))
+        return scores, rows
+
     def _buffers(self, b: int, k: int):
         if self._wire is None or (self._wire.b, self._wire.k) != (b, k):
             dev = self.local.device

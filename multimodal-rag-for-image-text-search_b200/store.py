@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import json
 import os
+import threading
 from dataclasses import dataclass
 from typing import Any, Dict, Iterable, List, Optional, Sequence
 
@@ -25,7 +26,9 @@ import numpy as np
 import torch
 
 from . import _native as N
-from .index import ResidentIndex
+from .durable import DurableLog
+from .hosttable import HostTable, make_arrow_table, rows_to_arrow
+from .index import MultiIndex, ResidentIndex
 from .versions import VersionFile
 
 
@@ -50,188 +53,287 @@ def _unit_f32(vector: Sequence[float]) -> np.ndarray:
     return arr / norm
 
 
+def _grow_filled(arr: np.ndarray, need: int, fill) -> np.ndarray:
+    if need <= arr.shape[0]:
+        return arr
+    out = np.full(max(need, int(arr.shape[0] * 1.5) + 1024), fill, dtype=arr.dtype)
+    out[: arr.shape[0]] = arr
+    return out
+
+
 class _Collection:
-    """Host master copy (columns in insertion order) + the resident copy on the GPU.
+    """Host master copy (`HostTable`: Arrow / numpy columns, O(new rows) per upsert) + the resident copy on the GPU.
 
     Resident layout = [base: tenant-sorted rows of the last compaction][delta segments appended since].  An upsert
     tombstones the replaced rows (their resident vectors are overwritten with NaN, which the kernels never
     return) and appends the new rows grouped by tenant, so a tenant owns a short list of row ranges and every
     search scans exactly those (mmr_search_ranges).  A compaction (full tenant-sorted rebuild) runs when the
-    buffer is full, tombstones exceed a quarter of it, or a tenant has collected more than MAX_RANGES ranges.
+    buffer is full, tombstones exceed a quarter of it, or a tenant has collected more than MAX_RANGES ranges; it
+    streams every host block once through the scatter loader (insertion order on the host, tenant order in HBM).
     This is the incremental refresh path of SURVEY 8f: an upsert no longer re-uploads the table.
+
+    With a `DurableLog` the collection is also the reader / writer of the shared on-disk state (durable.py): every
+    upsert batch becomes a delta file before the version is bumped, and `refresh()` pulls in what other processes wrote.
+
+    Thread safety: one re-entrant lock per collection serialises upserts, refreshes and searches (the resident
+    workspace, the staging buffers of mmr_search_host and the pending-delta lists are per collection).
     """
 
     MAX_RANGES = 8
     MAX_TOMB_FRACTION = 0.25
 
-    def __init__(self, name: str, device: torch.device, dtype: str) -> None:
+    def __init__(self, name: str, device: torch.device, dtype: str, log: Optional[DurableLog] = None,
+                 query_precision: str = "f32", devices: Optional[Sequence[torch.device]] = None) -> None:
+        # devices = the GPUs of one box the collection is row-range-sharded over (SURVEY 8e) -- ONE process, one shard
+        # and one launcher thread per device (index.MultiIndex).  Default: the single `device`.
+        self.devices = [torch.device(d) for d in devices] if devices else [device]
+        # "f32": what a request gets does not depend on which other requests shared its launch (the reference answers
+        # every request alone); "auto" lets same-tenant batches of >= 3 run on the tensor cores with 16-bit queries
+        self.query_precision = query_precision
         self.name = name
         self.device = device
         self.dtype = dtype
-        self.chunk_id: List[str] = []
-        self.user_id: List[str] = []
-        self.document_id: List[str] = []
-        self.modality: List[str] = []
-        self.meta: List[Optional[str]] = []
-        self._blocks: List[np.ndarray] = []     # f32 [n_i, D] blocks, concatenation = host row order
-        self._block_start: List[int] = []
-        self._alive: List[bool] = []
-        self._where: Dict[str, int] = {}        # chunk_id -> host row (alive rows only)
-        # resident state
+        self.host = HostTable(name)
+        self._lock = threading.RLock()
+        self._log = log
+        self._gen: Optional[int] = None
+        self._n_deltas = 0
+        self._stamp = None
+        self.rebuilds = 0
+        self.appends = 0
+        self.refreshes = 0
+        self.last_load_gbs: Optional[float] = None   # L1 loader throughput of the last compaction (fp32 bytes / s)
+        self._reset_resident()
+
+    def _reset_resident(self) -> None:
+        old = getattr(self, "_resident", None)
+        if old is not None:
+            old.close()
+        for sh in getattr(self, "_shards", []) or []:
+            sh.close()
+        multi = getattr(self, "_multi", None)
+        if multi is not None:
+            multi.close()
+        self._multi: Optional[MultiIndex] = None   # sharded form: G ResidentIndex shards behind one MultiIndex
+        self._shards: List[ResidentIndex] = []
+        self._bufs: List[torch.Tensor] = []
+        self._bounds: List[int] = []               # global resident row where each shard starts (+ end of the base)
         self._resident: Optional[ResidentIndex] = None
-        self._buf: Optional[torch.Tensor] = None   # capacity buffer [cap, D]
+        self._buf: Optional[torch.Tensor] = None   # capacity buffer [cap, D] (sharded: the LAST shard's buffer)
         self._n_res = 0
         self._perm = np.empty(0, np.int64)         # resident row -> host row
-        self._res_of: Dict[int, int] = {}          # host row -> resident row
+        self._res_of = np.empty(0, np.int64)       # host row -> resident row (-1 = not resident)
         self._ranges: Dict[str, List[List[int]]] = {}
         self._tomb = 0
-        self._pending_rows: List[int] = []         # host rows not yet resident
+        self._synced_upto = 0                      # host rows below this have been offered to the resident copy
         self._pending_tomb: List[int] = []         # resident rows to overwrite with NaN
         self._force_rebuild = True
         self._seg_key = None
-        self.rebuilds = 0
-        self.appends = 0
 
     # -- writes -------------------------------------------------------------------------------
     def __len__(self) -> int:
-        return len(self._where)
+        return len(self.host)
 
-    def _kill(self, host_row: int) -> None:
-        self._alive[host_row] = False           # table.delete("chunk_id == '...'") (lancedb_store.py:91-92)
-        res = self._res_of.pop(host_row, None)
-        if res is not None:
-            self._pending_tomb.append(res)
+    def host_row_of(self, chunk_id: str) -> int:
+        return int(self.host.find_alive([chunk_id])[0])
 
-    def _append(self, chunk_ids, user_ids, doc_ids, modalities, metas, emb: np.ndarray) -> None:
-        base = len(self.chunk_id)
-        emb = np.ascontiguousarray(emb, dtype=np.float32)
-        if self._blocks and emb.shape[1] != self._blocks[0].shape[1]:
-            raise ValueError(f"{self.name}: embedding length {emb.shape[1]} != {self._blocks[0].shape[1]} already stored")
-        self.chunk_id.extend(chunk_ids)
-        self.user_id.extend(user_ids)
-        self.document_id.extend(doc_ids)
-        self.modality.extend(modalities)
-        self.meta.extend(metas)
-        self._alive.extend([True] * len(chunk_ids))
-        for j, cid in enumerate(chunk_ids):
-            old = self._where.get(cid)
-            if old is not None:
-                # an id is a primary key everywhere else in the reference: the newest row wins (also inside a batch)
-                self._kill(old)
-            self._where[cid] = base + j
-        self._block_start.append(base)
-        self._blocks.append(emb)
-        self._pending_rows.extend(base + j for j in range(len(chunk_ids)) if self._alive[base + j])
+    def _host_rows(self, idx: np.ndarray) -> np.ndarray:
+        """f32 embeddings of the given host rows."""
+        return self.host.gather(np.asarray(idx, dtype=np.int64))
+
+    def _ingest(self, table) -> List[str]:
+        """Append an Arrow table (rows already unit-norm) to the host copy and queue the resident-side work."""
+        _, n, killed, users = self.host.append_table(table)
+        if n == 0:
+            return []
+        self._res_of = _grow_filled(self._res_of, self.host.n_total, -1)
+        if killed.size:                           # table.delete("chunk_id == '...'") (lancedb_store.py:91-92)
+            res = self._res_of[killed]
+            self._pending_tomb.extend(int(r) for r in res[res >= 0])
+            self._res_of[killed] = -1
+        return users
 
     def upsert(self, rows: Iterable[VectorRow]) -> List[str]:
         rows = list(rows)
         if not rows:
             return []
-        emb = [_unit_f32(r.embedding) for r in rows]
-        dims = {e.shape[0] for e in emb}
-        if len(dims) != 1:
-            raise ValueError(f"{self.name}: embeddings of different lengths in one upsert: {sorted(dims)}")
-        self._append([r.chunk_id for r in rows], [str(r.user_id) for r in rows], [r.document_id for r in rows],
-                     [r.modality for r in rows], [json.dumps(r.meta or {}) for r in rows], np.stack(emb))
-        return sorted({str(r.user_id) for r in rows})
+        try:
+            table = rows_to_arrow(rows, _unit_f32)
+        except ValueError as exc:
+            raise ValueError(f"{self.name}: {exc}") from None
+        return self.add_table(table)
 
-    def load_columns(self, chunk_ids, user_ids, doc_ids, modalities, metas, emb: np.ndarray) -> None:
-        """Bulk load of rows that are already normalised (what a LanceDB table holds)."""
-        self._append(list(chunk_ids), [str(u) for u in user_ids], list(doc_ids), list(modalities), list(metas), emb)
+    def add_table(self, table) -> List[str]:
+        """Upsert an Arrow table whose embeddings are already normalised (bulk load, or `upsert` after _prepare_rows).
+        With a durable log the batch is on disk (and named by the manifest) before this returns."""
+        if table.num_rows == 0:
+            return []
+        with self._lock:
+            if self._log is None:
+                return self._ingest(table)
+            with self._log.locked():
+                self.refresh()                    # another writer may have appended since we last looked
+                users = self._ingest(table)
+                self._log.append_delta(table)
+                self._n_deltas += 1
+                self._stamp = self._log.stamp()
+            return users
 
-    def _host_rows(self, idx: np.ndarray) -> np.ndarray:
-        """f32 embeddings of the given host rows."""
-        if len(self._blocks) > 1:
-            self._blocks = [np.concatenate(self._blocks, axis=0)]
-            self._block_start = [0]
-        return self._blocks[0][idx]
+    def refresh(self, force: bool = False, _depth: int = 0) -> List[str]:
+        """Pull in what other processes made durable since the last look.  One os.stat when nothing changed."""
+        if self._log is None:
+            return []
+        stamp = self._log.stamp()
+        if stamp == self._stamp and not force:
+            return []
+        users: List[str] = []
+        with self._lock:
+            m = self._log.manifest()
+            try:
+                if m["generation"] != self._gen:
+                    if self._gen is not None or self.host.n_total:
+                        self.host = HostTable(self.name)
+                        self._reset_resident()
+                    if m["base"]:
+                        users += self._ingest(self._log.read_table(m["base"]))
+                    self._gen, self._n_deltas = m["generation"], 0
+                for fname in m["deltas"][self._n_deltas:]:
+                    users += self._ingest(self._log.read_table(fname))
+                    self._n_deltas += 1
+            except FileNotFoundError:
+                if _depth >= 3:
+                    raise
+                self._gen = None                  # a compaction replaced the files under us: start over
+                return self.refresh(force=True, _depth=_depth + 1)
+            self._stamp = stamp
+            self.refreshes += 1
+        return sorted(set(users))
+
+    def persist(self) -> None:
+        """Durable compaction: all alive rows become the base of a new generation, delta files are dropped."""
+        if self._log is None:
+            raise ValueError("collection has no durable log")
+        with self._lock, self._log.locked():
+            self.refresh()
+            m = self._log.write_base(self.host.to_arrow())
+            self._gen, self._n_deltas = m["generation"], 0
+            self._stamp = self._log.stamp()
 
     # -- resident copy ------------------------------------------------------------------------
     def _rebuild(self) -> None:
         """Compaction: tenant-sorted base, no deltas, no tombstones."""
-        alive = np.nonzero(np.asarray(self._alive, dtype=bool))[0]
-        self._pending_rows, self._pending_tomb, self._tomb = [], [], 0
+        import time
+
+        host = self.host
+        alive = host.alive_rows()
+        self._reset_resident()
         self._force_rebuild = False
-        if self._resident is not None:
-            self._resident.close()
-            self._resident = None
-        if alive.size == 0:
-            self._buf, self._n_res, self._perm, self._res_of, self._ranges = None, 0, np.empty(0, np.int64), {}, {}
-            return
-        users = np.asarray(self.user_id, dtype=object)[alive].astype(str)
-        uniq, inv = np.unique(users, return_inverse=True)
-        order = np.argsort(inv, kind="stable")            # tenant-sorted, host order kept inside a tenant
-        self._perm = alive[order]
-        counts = np.bincount(inv, minlength=len(uniq))
-        seg = np.zeros(len(uniq) + 1, dtype=np.int64)
-        np.cumsum(counts, out=seg[1:])
+        self._synced_upto = host.n_total
+        self._res_of = np.full(host.n_total, -1, dtype=np.int64)
         n = int(alive.size)
+        if n == 0:
+            return
+        tenant = host.tenant[alive]
+        order = np.argsort(tenant, kind="stable")          # tenant-sorted, host order kept inside a tenant
+        perm = alive[order]
+        counts = np.bincount(tenant, minlength=len(host.tenants))
+        seg = np.zeros(len(host.tenants) + 1, dtype=np.int64)
+        np.cumsum(counts, out=seg[1:])
+        self._res_of[perm] = np.arange(n, dtype=np.int64)
         cap = max(n + 4096, int(n * 1.25))
-        base = ResidentIndex.from_f32(self._host_rows(self._perm), None, dtype=self.dtype, device=self.device)
-        self._buf = torch.empty((cap, base.dim), dtype=base.rows.dtype, device=self.device)
-        self._buf[:n].copy_(base.rows)
-        base.close()
+        self._perm = np.full(cap, -1, dtype=np.int64)       # sized like the capacity buffer: appends are O(new rows)
+        self._perm[:n] = perm
+        G = len(self.devices)
+        # row-range shards of the tenant-sorted order, balanced by rows; the last shard carries the append slack
+        self._bounds = [int(round(g * n / G)) for g in range(G)] + [n]
+        self._bufs = [ResidentIndex.alloc_rows((self._bounds[g + 1] - self._bounds[g]) if g < G - 1 else cap - self._bounds[g],
+                                               host.dim, self.dtype, self.devices[g]) for g in range(G)]
+        self._buf = self._bufs[-1]
+        t0 = time.perf_counter()
+        moved = 0
+        for blk in host.blocks:                             # each host block is read once per shard it lands in, in place
+            dst = self._res_of[blk.start:blk.start + blk.n]
+            live = dst[dst >= 0]
+            if live.size == 0:
+                continue
+            dmin, dmax = int(live.min()), int(live.max())
+            for g in range(G):
+                lo, hi = self._bounds[g], self._bounds[g + 1]
+                if dmax < lo or dmin >= hi:
+                    continue
+                local = dst if G == 1 else np.where((dst >= lo) & (dst < hi), dst - lo, -1)
+                ResidentIndex.load_rows_into(self._bufs[g], blk.emb, dst_rows=local)
+            moved += blk.n
+        dt = time.perf_counter() - t0
+        self.last_load_gbs = moved * host.dim * 4 / dt / 1e9 if dt > 0 else None
         self._n_res = n
-        self._resident = ResidentIndex(self._buf[:n])
-        self._resident.update(self._buf, n)
-        self._seg_key = None
-        self._res_of = {int(h): i for i, h in enumerate(self._perm)}
-        self._ranges = {str(u): [[int(seg[i]), int(seg[i + 1])]] for i, u in enumerate(uniq)}
+        self._shards = []
+        for g in range(G):
+            ng = self._bounds[g + 1] - self._bounds[g]
+            sh = ResidentIndex(self._bufs[g][:ng], row_base=self._bounds[g])
+            sh.update(self._bufs[g], ng)
+            sh.set_query_precision(self.query_precision)
+            self._shards.append(sh)
+        self._resident = self._shards[-1]
+        self._multi = MultiIndex(self._shards) if G > 1 else None
+        self._ranges = {host.tenants[i]: [[int(seg[i]), int(seg[i + 1])]] for i in range(len(host.tenants)) if counts[i]}
         self.rebuilds += 1
+
+    def _pending_rows(self) -> np.ndarray:
+        lo, hi = self._synced_upto, self.host.n_total
+        return np.nonzero(self.host.alive[lo:hi])[0] + lo
 
     def _apply_deltas(self) -> None:
         """Tombstone replaced rows and append the pending rows as per-tenant delta segments."""
         if self._pending_tomb:
-            idx = torch.as_tensor(self._pending_tomb, dtype=torch.int64, device=self.device)
-            self._buf.index_fill_(0, idx, float("nan"))
+            tomb = np.asarray(self._pending_tomb, dtype=np.int64)
+            G = len(self._bufs)
+            which = np.minimum(np.searchsorted(np.asarray(self._bounds[:G]), tomb, side="right") - 1, G - 1)
+            for g in np.unique(which):
+                idx = torch.as_tensor(tomb[which == g] - self._bounds[int(g)], dtype=torch.int64, device=self._bufs[int(g)].device)
+                self._bufs[int(g)].index_fill_(0, idx, float("nan"))
             self._tomb += len(self._pending_tomb)
             self._pending_tomb = []
-        rows = [h for h in self._pending_rows if self._alive[h]]
-        self._pending_rows = []
-        if rows:
-            rows = np.asarray(rows, dtype=np.int64)
-            users = np.asarray([self.user_id[h] for h in rows], dtype=object).astype(str)
-            order = np.argsort(users, kind="stable")       # group the batch by tenant, arrival order inside
-            rows, users = rows[order], users[order]
-            m = len(rows)
+        rows = self._pending_rows()
+        self._synced_upto = self.host.n_total
+        if rows.size:
+            tenant = self.host.tenant[rows]
+            order = np.argsort(tenant, kind="stable")      # group the batch by tenant, arrival order inside
+            rows, tenant = rows[order], tenant[order]
+            m = int(rows.size)
             lo = self._n_res
-            delta = ResidentIndex.from_f32(self._host_rows(rows), None, dtype=self.dtype, device=self.device)
-            self._buf[lo:lo + m].copy_(delta.rows)
-            delta.close()
-            self._perm = np.concatenate([self._perm, rows])
-            for j, h in enumerate(rows):
-                self._res_of[int(h)] = lo + j
-            start = 0
-            while start < m:
-                end = start
-                while end < m and users[end] == users[start]:
-                    end += 1
-                rl = self._ranges.setdefault(str(users[start]), [])
-                if rl and rl[-1][1] == lo + start:
-                    rl[-1][1] = lo + end                      # contiguous with the tenant's last range
+            ResidentIndex.load_rows_into(self._buf, self.host.gather(rows), dst_offset=lo - self._bounds[-2])
+            self._perm[lo:lo + m] = rows
+            self._res_of[rows] = lo + np.arange(m, dtype=np.int64)
+            cuts = np.nonzero(np.diff(tenant))[0] + 1
+            for start, end in zip(np.concatenate([[0], cuts]), np.concatenate([cuts, [m]])):
+                rl = self._ranges.setdefault(self.host.tenants[int(tenant[start])], [])
+                if rl and rl[-1][1] == lo + int(start):
+                    rl[-1][1] = lo + int(end)                 # contiguous with the tenant's last range
                 else:
-                    rl.append([lo + start, lo + end])
-                start = end
+                    rl.append([lo + int(start), lo + int(end)])
             self._n_res = lo + m
             self.appends += 1
-        self._resident.update(self._buf, self._n_res)
+        self._resident.update(self._buf, self._n_res - self._bounds[-2])   # (the last shard when sharded)
         self._seg_key = None
 
     def resident(self) -> Optional[ResidentIndex]:
-        if not self._force_rebuild and not self._pending_rows and not self._pending_tomb:
+        with self._lock:
+            dirty = self._synced_upto != self.host.n_total or self._pending_tomb
+            if not self._force_rebuild and not dirty:
+                return self._resident
+            n_new = int(self.host.alive[self._synced_upto:self.host.n_total].sum())
+            need_rebuild = (
+                self._force_rebuild or self._resident is None or self._buf is None
+                or self._n_res + n_new > self._bounds[-2] + self._buf.shape[0]
+                or (self._tomb + len(self._pending_tomb)) > self.MAX_TOMB_FRACTION * max(self._n_res, 1)
+                or any(len(r) >= self.MAX_RANGES for r in self._ranges.values())
+            )
+            if need_rebuild:
+                self._rebuild()
+            else:
+                self._apply_deltas()
             return self._resident
-        n_new = sum(1 for h in self._pending_rows if self._alive[h])
-        need_rebuild = (
-            self._force_rebuild or self._resident is None or self._buf is None
-            or self._n_res + n_new > self._buf.shape[0]
-            or (self._tomb + len(self._pending_tomb)) > self.MAX_TOMB_FRACTION * max(self._n_res, 1)
-            or any(len(r) >= self.MAX_RANGES for r in self._ranges.values())
-        )
-        if need_rebuild:
-            self._rebuild()
-        else:
-            self._apply_deltas()
-        return self._resident
 
     # -- reads --------------------------------------------------------------------------------
     def search_device(self, user_ids: Sequence[str], vectors: np.ndarray, top_k: int):
@@ -240,126 +342,124 @@ class _Collection:
         limit = max(int(top_k), 1)
         if limit > N.MMR_MAX_K:
             raise N.NativeError(f"top_k {limit} > {N.MMR_MAX_K}: not supported by the resident-index kernels")
-        res = self.resident()
-        if res is None:
-            return None
-        ranges = [self._ranges.get(str(u)) or [] for u in user_ids]
-        q = torch.from_numpy(np.ascontiguousarray(vectors, dtype=np.float32)).to(self.device)
-        return res.search_ranges(q, limit, ranges)
+        with self._lock:
+            res = self.resident()
+            if res is None:
+                return None
+            ranges = [self._ranges.get(str(u)) or [] for u in user_ids]
+            if self._multi is not None:       # sharded: merged host result -> the collector device (where K5 runs)
+                s, r = self._multi.search_host(np.ascontiguousarray(vectors, dtype=np.float32), limit, ranges)
+                return torch.from_numpy(s).to(self.devices[0]), torch.from_numpy(r).to(self.devices[0])
+            q = torch.from_numpy(np.ascontiguousarray(vectors, dtype=np.float32)).to(self.device)
+            return res.search_ranges(q, limit, ranges)
 
     def row_identity(self, resident_row: int) -> int:
         return int(self._perm[resident_row])
+
+    def chunk_id_of(self, resident_row: int) -> str:
+        return self.host.chunk_id_at(int(self._perm[resident_row]))
 
     def search(self, user_ids: Sequence[str], vectors: np.ndarray, top_k: int) -> List[List[Dict[str, Any]]]:
         limit = max(int(top_k), 1)
         if limit > N.MMR_MAX_K:
             raise N.NativeError(f"top_k {limit} > {N.MMR_MAX_K}: not supported by the resident-index kernels")
-        res = self.resident()
-        out: List[List[Dict[str, Any]]] = [[] for _ in user_ids]
-        if res is None:
+        with self._lock:
+            res = self.resident()
+            out: List[List[Dict[str, Any]]] = [[] for _ in user_ids]
+            if res is None:
+                return out
+            ranges = [self._ranges.get(str(u)) for u in user_ids]
+            live = [i for i, r in enumerate(ranges) if r]
+            if not live:
+                return out
+            q = np.ascontiguousarray(vectors[live], dtype=np.float32)
+            first = ranges[live[0]]
+            if self._multi is not None:
+                # row-range shards on the GPUs of this box: one launch per device, fused exchange, mapped mailbox
+                scores, rows = self._multi.search_host(q, limit, [ranges[i] for i in live])
+            elif len(first) == 1 and all(ranges[i] == first for i in live):
+                # one shared range: host-buffer C call (H2D + scan + D2H inside the library)
+                lo, hi = first[0]
+                if self._seg_key != (lo, hi, self._n_res):          # re-point the one-segment table only when it changes
+                    res.update(self._buf, self._n_res, seg_offsets=[lo, hi])
+                    self._seg_key = (lo, hi, self._n_res)
+                scores, rows = res.search_host(q, limit, [0] * len(live))
+            else:
+                s_dev, r_dev = res.search_ranges(torch.from_numpy(q).to(self.device), limit, [ranges[i] for i in live])
+                scores, rows = s_dev.cpu().numpy(), r_dev.cpu().numpy()
+            one = np.float32(1.0)
+            host, perm = self.host, self._perm
+            for j, i in enumerate(live):
+                hits = []
+                for s, r in zip(scores[j], rows[j]):
+                    if r < 0:
+                        break
+                    h = int(perm[r])
+                    distance = float(one - s)                 # Lance returns the f32 cosine distance
+                    hits.append({
+                        "chunk_id": host.chunk_id_at(h),
+                        "score": 1.0 - distance,              # _format_results (:130-131)
+                        "meta": json.loads(host.meta_at(h) or "{}"),
+                    })
+                out[i] = hits
             return out
-        ranges = [self._ranges.get(str(u)) for u in user_ids]
-        live = [i for i, r in enumerate(ranges) if r]
-        if not live:
-            return out
-        q = np.ascontiguousarray(vectors[live], dtype=np.float32)
-        if all(len(ranges[i]) == 1 and ranges[i] == ranges[live[0]] for i in live):
-            # one shared range: host-buffer C call (H2D + scan + D2H inside the library)
-            lo, hi = ranges[live[0]][0]
-            if self._seg_key != (lo, hi, self._n_res):          # re-point the one-segment table only when it changes
-                res.update(self._buf, self._n_res, seg_offsets=[lo, hi])
-                self._seg_key = (lo, hi, self._n_res)
-            scores, rows = res.search_host(q, limit, [0] * len(live))
-        else:
-            s_dev, r_dev = res.search_ranges(torch.from_numpy(q).to(self.device), limit, [ranges[i] for i in live])
-            scores, rows = s_dev.cpu().numpy(), r_dev.cpu().numpy()
-        one = np.float32(1.0)
-        for j, i in enumerate(live):
-            hits = []
-            for s, r in zip(scores[j], rows[j]):
-                if r < 0:
-                    break
-                h = int(self._perm[r])
-                distance = float(one - s)                 # Lance returns the f32 cosine distance
-                hits.append({
-                    "chunk_id": self.chunk_id[h],
-                    "score": 1.0 - distance,              # _format_results (:130-131)
-                    "meta": json.loads(self.meta[h] or "{}"),
-                })
-            out[i] = hits
-        return out
 
 
 class B200Store:
-    """Drop-in for `app.ml.retrieve._LANCEDB_STORE` / `app.ml.index_build._LANCEDB_STORE`."""
+    """Drop-in for `app.ml.retrieve._LANCEDB_STORE` / `app.ml.index_build._LANCEDB_STORE`.
 
-    def __init__(self, db_path: Optional[str] = None, device: Any = "cuda:0", dtype: str = "bf16") -> None:
+    `db_path` (the reference's LanceDB directory, lancedb_store.py:27-29) makes the store durable and shared: every
+    upsert batch is written as an Arrow delta file before `index_versions.json` is bumped, and a store in ANOTHER
+    process on the same directory sees it on its next call (it polls the manifest stamps; reference deployment:
+    Celery writer + API reader, docker-compose.yml:36-45).  Without `db_path` the store lives in memory only.
+    """
+
+    def __init__(self, db_path: Optional[str] = None, device: Any = "cuda:0", dtype: str = "bf16",
+                 devices: Optional[Sequence[Any]] = None, query_precision: str = "f32") -> None:
+        """devices=[0, 1, ..., 7]: row-range-shard every collection over those GPUs of this box (one process; the same
+        search_* calls; results bit-identical to one GPU).  query_precision: see _Collection."""
         N.lib()  # fail now, loudly, if the CUDA library is missing
         if not torch.cuda.is_available():
             raise N.NativeError("no CUDA device: B200Store has no CPU fallback")
-        self._device = torch.device(device)
+        devs = [torch.device("cuda", d) if isinstance(d, int) else torch.device(d) for d in devices] if devices else None
+        self._init_state(db_path, devs[0] if devs else torch.device(device), dtype, devs, query_precision)
+
+    def _init_state(self, db_path: Optional[str], device: torch.device, dtype: str, devices=None,
+                    query_precision: str = "f32") -> None:
+        self._device = device
         self._db_path = db_path
-        self._text_table = _Collection("text_collection", self._device, dtype)
-        self._image_table = _Collection("image_collection", self._device, dtype)
-        self._versions = VersionFile(os.path.join(db_path, "index_versions.json") if db_path else None)
         if db_path:
-            # durable state next to index_versions.json: one Arrow IPC file per collection with the reference schema
-            # (what LanceDB keeps as .lance fragments); a restarted process reloads them into HBM
-            for coll in (self._text_table, self._image_table):
-                path = os.path.join(db_path, coll.name + ".arrow")
-                if os.path.exists(path):
-                    self._load_ipc(coll, path)
+            os.makedirs(db_path, exist_ok=True)
 
-    @staticmethod
-    def _load_ipc(coll: "_Collection", path: str) -> None:
-        import pyarrow as pa
-        import pyarrow.ipc as ipc
+        def log(name):
+            return DurableLog(db_path, name) if db_path else None
 
-        with pa.memory_map(path, "r") as src:
-            table = ipc.open_file(src).read_all()
-        if table.num_rows:
-            B200Store._load_table(coll, table)
+        self._text_table = _Collection("text_collection", device, dtype, log("text_collection"), query_precision, devices)
+        self._image_table = _Collection("image_collection", device, dtype, log("image_collection"), query_precision, devices)
+        self._versions = VersionFile(os.path.join(db_path, "index_versions.json") if db_path else None)
+        self._sync()   # durable state next to index_versions.json: a restarted process reloads it into HBM
 
-    @staticmethod
-    def _load_table(coll: "_Collection", table) -> List[str]:
-        emb = table.column("embedding").combine_chunks()
-        offsets = emb.offsets.to_numpy()
-        widths = np.diff(offsets)
-        if widths.size and (widths != widths[0]).any():
-            raise ValueError(f"{coll.name}: variable-length embeddings are not supported by the resident scan")
-        flat = emb.values.to_numpy(zero_copy_only=False)[offsets[0]:offsets[-1]]
-        mat = np.ascontiguousarray(flat, dtype=np.float32).reshape(table.num_rows, int(widths[0]))
-        cols = {c: table.column(c).to_pylist() for c in ("chunk_id", "user_id", "document_id", "modality", "meta")}
-        coll.load_columns(cols["chunk_id"], cols["user_id"], cols["document_id"], cols["modality"], cols["meta"], mat)
-        return sorted(set(map(str, cols["user_id"])))
+    def _sync(self) -> None:
+        """Cross-process invalidation: pick up what other processes made durable (two os.stat calls when idle)."""
+        self._text_table.refresh()
+        self._image_table.refresh()
+
+    def _collection(self, name: str) -> _Collection:
+        return {"text_collection": self._text_table, "image_collection": self._image_table}[name]
 
     def load_arrow_ipc(self, collection: str, path: str) -> None:
         """Bulk-load an Arrow IPC file written with the reference schema (see make_arrow_table / persist)."""
         import pyarrow as pa
         import pyarrow.ipc as ipc
 
-        with pa.memory_map(path, "r") as src:
-            self.load_arrow(collection, ipc.open_file(src).read_all())
+        self.load_arrow(collection, ipc.open_file(pa.memory_map(path, "r")).read_all())
 
     def persist(self) -> None:
-        """Write both collections (live rows, host order) as Arrow IPC files under db_path."""
-        import pyarrow as pa
-        import pyarrow.ipc as ipc
-
+        """Durable compaction of both collections (alive rows -> new base generation, delta files dropped)."""
         if not self._db_path:
             raise ValueError("B200Store was created without a db_path")
-        os.makedirs(self._db_path, exist_ok=True)
         for coll in (self._text_table, self._image_table):
-            alive = np.nonzero(np.asarray(coll._alive, dtype=bool))[0]
-            if alive.size == 0:
-                continue
-            table = make_arrow_table([coll.chunk_id[i] for i in alive], [coll.user_id[i] for i in alive],
-                                     [coll.document_id[i] for i in alive], [coll.modality[i] for i in alive],
-                                     coll._host_rows(alive), [coll.meta[i] for i in alive])
-            tmp = os.path.join(self._db_path, coll.name + ".arrow.tmp")
-            with pa.OSFile(tmp, "wb") as sink, ipc.new_file(sink, table.schema) as writer:
-                writer.write_table(table)
-            os.replace(tmp, os.path.join(self._db_path, coll.name + ".arrow"))
+            coll.persist()
 
     # writes (lancedb_store.py:87-101) + version bump (index_build.py:102,148)
     def upsert_text_vectors(self, rows: Iterable[VectorRow]) -> None:
@@ -375,27 +475,29 @@ class B200Store:
 
     def load_arrow(self, collection: str, table) -> None:
         """Bulk-load a pyarrow Table with the reference schema (chunk_id, user_id, document_id, modality,
-        embedding: list<float32>, meta) -- what `lancedb.Table.to_arrow()` yields."""
-        coll = {"text_collection": self._text_table, "image_collection": self._image_table}[collection]
-        if table.num_rows == 0:
-            return
-        for user in self._load_table(coll, table):
+        embedding: list<float32>, meta) -- what `lancedb.Table.to_arrow()` yields.  The embedding column is used in
+        place (zero-copy) as the host master copy."""
+        for user in self._collection(collection).add_table(table):
             self._versions.bump(user)
 
     # reads (lancedb_store.py:103-123)
     def search_text(self, user_id: str, query_vec: Sequence[float], top_k: int) -> List[Dict[str, Any]]:
+        self._text_table.refresh()
         q = np.asarray(query_vec, dtype=np.float32)[None, :]
         return self._text_table.search([user_id], q, top_k)[0]
 
     def search_image(self, user_id: str, query_vec: Sequence[float], top_k: int) -> List[Dict[str, Any]]:
+        self._image_table.refresh()
         q = np.asarray(query_vec, dtype=np.float32)[None, :]
         return self._image_table.search([user_id], q, top_k)[0]
 
     # micro-batched requests: one launch for B (tenant, query) pairs
     def search_text_batch(self, user_ids: Sequence[str], query_vecs, top_k: int) -> List[List[Dict[str, Any]]]:
+        self._text_table.refresh()
         return self._text_table.search(list(user_ids), np.asarray(query_vecs, dtype=np.float32), top_k)
 
     def search_image_batch(self, user_ids: Sequence[str], query_vecs, top_k: int) -> List[List[Dict[str, Any]]]:
+        self._image_table.refresh()
         return self._image_table.search(list(user_ids), np.asarray(query_vecs, dtype=np.float32), top_k)
 
     def fused_search_batch(self, user_ids: Sequence[str], text_vecs, image_vecs, top_k_text: int, top_k_image: int,
@@ -404,6 +506,7 @@ class B200Store:
         CONFIDENCE_TAU gate (kernels K1/K2 + K5).  Returns per request ([{"chunk_id", "modality", "score",
         "combined_score"}, ...] best first, low_confidence flag) -- what retrieve() then _confidence_low() give when
         every hit survives the metadata join (reference app/ml/retrieve.py:103-117, app/ml/generate.py:56-60)."""
+        self._sync()
         return _fused_batch(self, list(user_ids), text_vecs, image_vecs, top_k_text, top_k_image, final_n, tau)
 
 
@@ -425,27 +528,7 @@ def _fused_batch(store: "B200Store", user_ids, text_vecs, image_vecs, kt: int, k
             if rows[b, o] < 0:
                 break
             coll = store._text_table if mod[b, o] == 0 else store._image_table
-            h = coll.row_identity(int(rows[b, o]))
-            items.append({"chunk_id": coll.chunk_id[h], "modality": "text" if mod[b, o] == 0 else "image",
+            items.append({"chunk_id": coll.chunk_id_of(int(rows[b, o])), "modality": "text" if mod[b, o] == 0 else "image",
                           "score": float(score[b, o]), "combined_score": float(comb[b, o])})
         results.append((items, bool(low[b])))
     return results
-
-
-def make_arrow_table(chunk_ids, user_ids, document_ids, modalities, embeddings: np.ndarray, metas):
-    """A pyarrow Table with exactly the reference schema (lancedb_store.py:33-44); fixture / export helper."""
-    import pyarrow as pa
-
-    emb = np.ascontiguousarray(embeddings, dtype=np.float32)
-    n, d = emb.shape
-    offsets = pa.array(np.arange(0, (n + 1) * d, d, dtype=np.int32))
-    lst = pa.ListArray.from_arrays(offsets, pa.array(emb.reshape(-1), type=pa.float32()))
-    schema = pa.schema([
-        pa.field("chunk_id", pa.string()), pa.field("user_id", pa.string()), pa.field("document_id", pa.string()),
-        pa.field("modality", pa.string()), pa.field("embedding", pa.list_(pa.float32())),
-        pa.field("meta", pa.string(), nullable=True),
-    ])
-    return pa.Table.from_arrays(
-        [pa.array(list(chunk_ids), pa.string()), pa.array(list(user_ids), pa.string()),
-         pa.array(list(document_ids), pa.string()), pa.array(list(modalities), pa.string()), lst,
-         pa.array(list(metas), pa.string())], schema=schema)

@@ -213,7 +213,7 @@ def test_incremental_upserts_track_the_oracle_store(mmr):
         old_vec = None
         if step == 2:
             victim = over[0]
-            hr = gpu._text_table._where[victim.chunk_id]
+            hr = gpu._text_table.host_row_of(victim.chunk_id)
             old_vec = gpu._text_table._host_rows(np.array([hr]))[0].copy()
         for st in (gpu, cpu):
             st.upsert_text_vectors([mmr.VectorRow(**r.__dict__) for r in batch] if st is gpu else batch)
@@ -415,7 +415,9 @@ def test_persist_and_restart(mmr, tmp_path):
     s1.upsert_image_vectors([mmr.VectorRow(**r.__dict__) for r in rows_i])
     s1.upsert_text_vectors([mmr.VectorRow(**rows_t[3].__dict__)])        # an overwrite: only the live copy is persisted
     s1.persist()
-    assert sorted(os.listdir(db)) == ["image_collection.arrow", "index_versions.json", "text_collection.arrow"]
+    files = sorted(f for f in os.listdir(db) if not f.endswith(".lock"))
+    assert files == ["image_collection.g1.base.arrow", "image_collection.manifest.json", "index_versions.json",
+                     "text_collection.g1.base.arrow", "text_collection.manifest.json"], files
     s2 = mmr.B200Store(db)
     assert len(s2._text_table) == 1500 and len(s2._image_table) == 700
     assert s2.get_index_version("a") == s1.get_index_version("a") >= 2
@@ -425,7 +427,44 @@ def test_persist_and_restart(mmr, tmp_path):
         assert s2.search_text(u, qt.tolist(), 20) == s1.search_text(u, qt.tolist(), 20)
         assert s2.search_image(u, qi.tolist(), 12) == s1.search_image(u, qi.tolist(), 12)
     import pyarrow as pa, pyarrow.ipc as ipc
-    with pa.memory_map(os.path.join(db, "text_collection.arrow"), "r") as src:
+    with pa.memory_map(os.path.join(db, "text_collection.g1.base.arrow"), "r") as src:
         schema = ipc.open_file(src).schema
     assert [f.name for f in schema] == ["chunk_id", "user_id", "document_id", "modality", "embedding", "meta"]
     assert str(schema.field("embedding").type) == "list<item: float>"
+
+
+def _gpu_writer(db, seed, lo, hi):
+    import importlib
+    m = importlib.import_module("multimodal-rag-for-image-text-search_b200")
+    st = m.B200Store(db)
+    rows = _rows(hi - lo, 512, seed, ["alice", "bob"], f"w{seed}_")
+    st.upsert_image_vectors([m.VectorRow(**r.__dict__) for r in rows])
+
+
+def test_writer_process_upsert_is_visible_to_reader_process(mmr, tmp_path):
+    """The reference's deployment: a Celery worker upserts (app/tasks.py:108,165), the API process searches
+    (app/ml/retrieve.py:21); they meet on disk.  Here: a second PROCESS with its own B200Store writes, this process's
+    store -- created before -- returns the new rows on its next call and uploads only the delta."""
+    import multiprocessing as mp
+    db = str(tmp_path / "lance_db")
+    reader = mmr.B200Store(db)
+    base = _rows(3000, 512, 41, ["alice", "bob"], "b")
+    reader.upsert_image_vectors([mmr.VectorRow(**r.__dict__) for r in base])
+    q = np.random.default_rng(42).standard_normal(512).astype(np.float32)
+    before = reader.search_image("alice", q.tolist(), 12)
+    assert len(before) == 12 and reader._image_table.rebuilds == 1
+    ctx = mp.get_context("spawn")
+    p = ctx.Process(target=_gpu_writer, args=(db, 43, 0, 400))
+    p.start(); p.join(300)
+    assert p.exitcode == 0
+    v0 = reader.get_index_version("alice")
+    after = reader.search_image("alice", q.tolist(), 12)
+    assert reader._image_table.rebuilds == 1 and reader._image_table.appends == 1      # delta only, no re-upload
+    assert len(reader._image_table) == 3400 and v0 == 2
+    fresh = mmr.B200Store(db)
+    assert fresh.search_image("alice", q.tolist(), 12) == after
+    # the planted neighbour written by the other process comes back first
+    new_rows = _rows(400, 512, 43, ["alice", "bob"], "w43_")
+    target = next(r for r in new_rows if r.user_id == "alice")
+    top = reader.search_image("alice", list(target.embedding), 1)
+    assert top[0]["chunk_id"] == target.chunk_id and top[0]["score"] > 0.99

@@ -216,7 +216,7 @@ def test_pipelined_launches_give_identical_results(mmr, monkeypatch):
     torch.cuda.synchronize()
     results = {}
     for mode in ("0", "1"):
-        monkeypatch.setenv("MMR_PDL", mode)
+        mmr._native.set_option("MMR_PDL", mode)
         outs = [(torch.empty((1, 10), dtype=torch.float32, device="cuda"), torch.empty((1, 10), dtype=torch.int64, device="cuda"))
                 for _ in range(64)]
         for rep in range(3):
@@ -224,6 +224,7 @@ def test_pipelined_launches_give_identical_results(mmr, monkeypatch):
                 ix.search(qs[i:i + 1], 10, out=outs[i])
         torch.cuda.synchronize()
         results[mode] = (torch.cat([o[0] for o in outs]).cpu(), torch.cat([o[1] for o in outs]).cpu())
+    mmr._native.set_option("MMR_PDL", None)
     assert torch.equal(results["0"][1], results["1"][1])
     assert torch.equal(results["0"][0], results["1"][0])
     for i in (0, 17, 63):

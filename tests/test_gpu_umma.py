@@ -27,9 +27,13 @@ def _bf16(x):
 def umma_mode(request, monkeypatch):
     """ts = query tile as the A operand in tensor memory; ss = both operands in shared memory;
     pair = ts on CTA pairs (tcgen05.mma.cta_group::2, M = 256) for batches of at least two query tiles."""
-    monkeypatch.setenv("MMR_UMMA_MODE", "ts" if request.param == "pair" else request.param)
-    monkeypatch.setenv("MMR_UMMA_PAIR", "1" if request.param == "pair" else "0")
-    return request.param
+    import importlib
+    native = importlib.import_module("multimodal-rag-for-image-text-search_b200._native")
+    native.set_option("MMR_UMMA_MODE", "ts" if request.param == "pair" else request.param)
+    native.set_option("MMR_UMMA_PAIR", "1" if request.param == "pair" else "0")
+    yield request.param
+    native.set_option("MMR_UMMA_MODE", None)
+    native.set_option("MMR_UMMA_PAIR", None)
 
 
 @pytest.mark.parametrize("dim", [512, 384])
