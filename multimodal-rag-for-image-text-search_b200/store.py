@@ -184,7 +184,7 @@ class _Collection:
         if self._log is None:
             return []
         stamp = self._log.stamp()
-        if stamp == self._stamp and not force:
+        if stamp == self._stamp and not force and self._gen is not None:
             return []
         users: List[str] = []
         with self._lock:
@@ -389,19 +389,20 @@ class _Collection:
                 scores, rows = s_dev.cpu().numpy(), r_dev.cpu().numpy()
             one = np.float32(1.0)
             host, perm = self.host, self._perm
+            valid = rows >= 0                                   # hits are a prefix of every result row
+            counts = valid.sum(axis=1)
+            hrows = perm[rows[valid]]                           # host rows of every hit of the batch, one gather
+            ids = host.values_at("chunk_id", hrows)
+            metas = host.values_at("meta", hrows)
+            # Lance returns the f32 cosine distance; _format_results (:130-131) turns it into a Python float score
+            sims = (1.0 - (one - scores[valid]).astype(np.float64)).tolist()
+            pos = 0
             for j, i in enumerate(live):
-                hits = []
-                for s, r in zip(scores[j], rows[j]):
-                    if r < 0:
-                        break
-                    h = int(perm[r])
-                    distance = float(one - s)                 # Lance returns the f32 cosine distance
-                    hits.append({
-                        "chunk_id": host.chunk_id_at(h),
-                        "score": 1.0 - distance,              # _format_results (:130-131)
-                        "meta": json.loads(host.meta_at(h) or "{}"),
-                    })
-                out[i] = hits
+                c = int(counts[j])
+                out[i] = [{"chunk_id": ids[p], "score": sims[p],
+                           "meta": {} if metas[p] in (None, "", "{}") else json.loads(metas[p])}
+                          for p in range(pos, pos + c)]
+                pos += c
             return out
 
 
