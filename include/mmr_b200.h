@@ -221,6 +221,47 @@ int mmr_fuse_f64(const double* text_scores_dev, const int32_t* text_count_dev, c
                  int32_t* out_index_dev, uint8_t* out_low_conf_dev, void* stream);
 
 /*
+ * Query encoders on the device: the models in front of and behind the scan, so that a query is
+ * born on the GPU and its embedding feeds mmr_search without a host hop.
+ *   MMR_ENC_MINILM     embed_text_batch: MiniLM-L6 (BERT, post-LN), masked mean pooling, L2 norm -> [B, hidden]
+ *                      (reference app/ml/embeddings.py:52-70, sentence-transformers/all-MiniLM-L6-v2)
+ *   MMR_ENC_CLIP_TEXT  embed_query_for_images: CLIP text tower (pre-LN, causal), hidden state at the EOS token -> final
+ *                      LayerNorm -> text_projection -> L2 norm -> [B, proj_dim]   (app/ml/embeddings.py:94-105)
+ *   MMR_ENC_CROSS      CrossEncoder.predict: the same BERT + pooler (tanh) + 1-logit classifier -> [B] raw logits
+ *                      (app/ml/retrieve.py:29-38,146; cross-encoder/ms-marco-MiniLM-L-6-v2)
+ * Tokenisation stays with the caller (HF tokenizers need the vocabulary files): the calls take token ids.
+ * Weights are handed over once, by name, as fp32 device arrays in nn.Linear layout ([out, in]); GEMM weights are kept
+ * as bf16, everything else as fp32:
+ *   word_emb pos_emb type_emb emb_ln_w emb_ln_b | L<i>.qkv_w ([3H, H]: q, k, v stacked) L<i>.qkv_b L<i>.o_w L<i>.o_b
+ *   L<i>.ln1_w L<i>.ln1_b L<i>.fc1_w L<i>.fc1_b L<i>.fc2_w L<i>.fc2_b L<i>.ln2_w L<i>.ln2_b | final_ln_w final_ln_b proj_w
+ *   (CLIP) | pooler_w pooler_b cls_w cls_b (cross-encoder).  ln1 / ln2 are the first / second LayerNorm of a layer.
+ */
+enum mmr_encoder_kind { MMR_ENC_MINILM = 0, MMR_ENC_CLIP_TEXT = 1, MMR_ENC_CROSS = 2 };
+typedef struct mmr_encoder_config {
+  int32_t kind;           /* enum mmr_encoder_kind */
+  int32_t vocab_size;
+  int32_t hidden;         /* 384 (MiniLM) or 512 (CLIP) */
+  int32_t layers;
+  int32_t heads;          /* head dim 32 or 64 */
+  int32_t intermediate;   /* multiple of 128 */
+  int32_t max_positions;
+  int32_t type_vocab;     /* BERT token types (2); ignored for CLIP */
+  int32_t proj_dim;       /* CLIP text_projection rows; ignored otherwise */
+  int32_t eos_token_id;   /* CLIP pooling position (first occurrence; 2 = legacy argmax rule) */
+  float ln_eps;
+} mmr_encoder_config;
+typedef struct mmr_encoder mmr_encoder;
+int mmr_encoder_create(int device, const mmr_encoder_config* config, mmr_encoder** out);
+int mmr_encoder_destroy(mmr_encoder* encoder);
+int mmr_encoder_out_dim(const mmr_encoder* encoder);
+int mmr_encoder_set_weight(mmr_encoder* encoder, const char* name, const float* data_dev, int64_t numel, void* stream);
+/* One forward pass for B sequences padded to S tokens (S <= 512).  ids / mask (1 = token, 0 = padding; NULL = all ones) /
+ * token types (NULL = all zero) are HOST arrays [B, S]; out_dev is [B, out_dim] fp32 on the encoder's device
+ * (L2-normalised embeddings, or [B] logits for MMR_ENC_CROSS) -- directly usable as mmr_search's queries_dev. */
+int mmr_encoder_forward(mmr_encoder* encoder, const int32_t* input_ids_host, const int32_t* attention_mask_host,
+                        const int32_t* token_type_host, int32_t B, int32_t S, float* out_dev, void* stream);
+
+/*
  * Validation hook for the tensor-core path (K2): raw cosine scores of B queries against rows
  * [row_begin, row_end) as computed by the tcgen05 contraction (bf16 queries x bf16 rows, fp32 accumulate),
  * written to out_scores_dev[b * out_ld + (row - row_begin)].  workspace as for mmr_search(B, k = 10).

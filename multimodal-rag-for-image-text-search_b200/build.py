@@ -10,7 +10,7 @@ from typing import List
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmmr_b200.so")
-SOURCES = ["mmr_b200.cu"]
+SOURCES = ["mmr_b200.cu", "mmr_encoder.cu"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -37,21 +37,37 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False, extra: List[str] | None = None) -> str:
-    """Compile csrc/*.cu -> libmmr_b200.so.  Returns the library path."""
+    """Compile csrc/*.cu -> libmmr_b200.so (one nvcc per translation unit, in parallel, then one link).  Returns the
+    library path."""
+    from concurrent.futures import ThreadPoolExecutor
+
     if not force and not needs_build():
         return LIB
     defines = ["-DMMR_WITH_UMMA"] if os.path.exists(os.path.join(CSRC, "scan_umma.cuh")) else []
-    cmd = [
-        _nvcc(), *ARCH_FLAGS, "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
-        *defines, *(extra or []), "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES],
-    ]
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    common = [_nvcc(), *ARCH_FLAGS, "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", *defines, *(extra or [])]
+
+    def compile_one(src: str) -> str:
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        cmd = [*common, "-c", "-o", obj, os.path.join(CSRC, src)]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
+        if verbose and (res.stdout or res.stderr):
+            print(res.stdout + res.stderr, file=sys.stderr)
+        return obj
+
+    with ThreadPoolExecutor(len(SOURCES)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
+    link = [_nvcc(), *ARCH_FLAGS, "-shared", "-o", LIB, *objs]
     if verbose:
-        print(" ".join(cmd), file=sys.stderr)
-    res = subprocess.run(cmd, capture_output=True, text=True)
+        print(" ".join(link), file=sys.stderr)
+    res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose and (res.stdout or res.stderr):
-        print(res.stdout + res.stderr, file=sys.stderr)
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     return LIB
 
 

@@ -52,6 +52,8 @@ struct Options {
   int umma_noprobe = 0;   // MMR_UMMA_NOPROBE=1
   int force_family = 0;   // MMR_FORCE_FAMILY 1 = K1, 2 = K2 regardless of batch size
   int umma_quad = 1;      // MMR_UMMA_QUAD=0  no 4-CTA multicast clusters
+  int inline_query = 1;   // MMR_INLINE_QUERY=0  host-buffer calls always stage the query with an H2D copy (measurement)
+  int mailbox = 1;        // MMR_MAILBOX=0       host-buffer calls synchronise the stream instead of spinning on the flag
 };
 inline Options& options() {
   static Options o;

@@ -1,0 +1,416 @@
+// Query encoders on the device: the transformer kernels behind
+//   embed_text_batch        (MiniLM-L6: BERT, 6 layers, hidden 384, mean pooling, L2 norm)   reference app/ml/embeddings.py:52-70
+//   embed_query_for_images  (CLIP ViT-B/32 text tower: 12 pre-LN layers, hidden 512, causal, EOS pooling, projection, L2 norm)
+//                                                                                              reference app/ml/embeddings.py:94-105
+//   CrossEncoder.predict    (ms-marco-MiniLM-L-6: the same BERT + pooler + 1-logit classifier) reference app/ml/retrieve.py:132-155
+// so that a query is born on the GPU and feeds mmr_search directly.
+//
+// These models are small and latency-bound (a query is 8-40 tokens; 21 / 75 MB of bf16 weights stay in L2), so the
+// kernels are shaped for short sequences and batch <= 128:
+//   * every linear layer is ONE "swap-AB" tcgen05 GEMM: the WEIGHT tile is the 128-row M operand (features = TMEM lanes),
+//     the tokens are the N operand (64 per tile), so a 16-token query still fills the tensor-core tile's M side and the
+//     epilogue thread owns one output feature (bias / activation / residual without cross-lane traffic);
+//     weights [N_out, K] bf16 are exactly nn.Linear's layout = K-major: TMA boxes with 128B swizzle, no transposes;
+//   * attention is per (sequence, head) on CUDA cores in fp32 (S <= 512, head dim 32 / 64): K and V of the head live in
+//     shared memory, one warp per query row;
+//   * LayerNorm / embedding / pooling are warp-per-row fp32 kernels; the residual stream stays fp32, only GEMM inputs
+//     are bf16.
+// All kernels chain with programmatic dependent launch (pdl_chain_prologue) so the ~45 launches of a forward pass do not
+// pay a launch gap each.
+#pragma once
+#include "scan_umma.cuh"
+
+namespace mmr {
+
+constexpr int ENC_THREADS = 192;
+constexpr int ENC_BM = 128;   // output features per tile (UMMA M)
+constexpr int ENC_NT = 64;    // tokens per tile (UMMA N)
+constexpr int ENC_W_SLICE = ENC_BM * 128;  // 16 KB: [128 features x 64 bf16]
+constexpr int ENC_X_SLICE = ENC_NT * 128;  //  8 KB: [64 tokens   x 64 bf16]
+constexpr int ENC_MAX_STAGES = 8;
+
+enum GemmEpilogue { EPI_BIAS_F32 = 0, EPI_BIAS_RES_F32 = 1, EPI_GELU_BF16 = 2, EPI_QUICKGELU_BF16 = 3 };
+
+struct GemmParams {
+  int32_t M, N, K;            // tokens, output features, input features
+  int32_t nstages;
+  const float* bias;          // [N]
+  const float* residual;      // [M, N] fp32 (EPI_BIAS_RES_F32)
+  float* out_f32;             // [M, N]
+  __nv_bfloat16* out_bf16;    // [M, N]
+};
+
+#ifdef __CUDACC__
+__host__ __device__ constexpr uint32_t enc_idesc() {  // kind::f16, bf16 x bf16 -> f32, M = 128, N = 64, both K-major
+  return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(ENC_NT >> 3) << 17) | (uint32_t(ENC_BM >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_alloc_cols(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cols(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
+
+// out[t, f] = epilogue( sum_k X[t, k] * W[f, k] + bias[f] )      grid = (N / 128, ceil(M / 64))
+template <int EPI>
+__global__ void __launch_bounds__(ENC_THREADS, 1)
+gemm_wt_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x, const GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_chain_prologue();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nst = p.nstages;
+  const int ks = p.K / 64;
+  const uint32_t w_s = smem_u32(smem);                              // [nst][16 KB]
+  const uint32_t x_s = w_s + uint32_t(nst) * ENC_W_SLICE;           // [nst][ 8 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(nst) * (ENC_W_SLICE + ENC_X_SLICE));
+  const uint32_t bar_full = smem_u32(bars);
+  const uint32_t bar_empty = bar_full + ENC_MAX_STAGES * 8;
+  const uint32_t bar_acc = bar_empty + ENC_MAX_STAGES * 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ENC_MAX_STAGES + 1);
+  const int f0 = blockIdx.x * ENC_BM;
+  const int t0 = blockIdx.y * ENC_NT;
+
+  if (threadIdx.x == 0) {
+    if ((w_s & 1023u) != 0) __trap();
+    for (int s = 0; s < ENC_MAX_STAGES; ++s) {
+      mbar_init(bar_full + s * 8, 1);
+      mbar_init(bar_empty + s * 8, 1);
+    }
+    mbar_init(bar_acc, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_x);
+  }
+  if (warp == 1) tmem_alloc_cols(smem_u32(tmem_slot), ENC_NT);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int s = 0; s < ks; ++s) {
+      mbar_wait(bar_empty + stage * 8, phase ^ 1u);
+      if (leader) {
+        mbar_arrive_expect_tx(bar_full + stage * 8, ENC_W_SLICE + ENC_X_SLICE);
+        tma_load_2d(w_s + stage * ENC_W_SLICE, &tm_w, bar_full + stage * 8, s * 64, f0);
+        tma_load_2d(x_s + stage * ENC_X_SLICE, &tm_x, bar_full + stage * 8, s * 64, t0);   // rows past M are zero-filled
+      }
+      __syncwarp();
+      if (++stage == nst) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = elect_one();
+    const uint32_t idesc = enc_idesc();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int s = 0; s < ks; ++s) {
+      mbar_wait(bar_full + stage * 8, phase);
+      tc_fence_after();
+      const uint64_t a_desc = umma_smem_desc(w_s + stage * ENC_W_SLICE);
+      const uint64_t b_desc = umma_smem_desc(x_s + stage * ENC_X_SLICE);
+      if (leader) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_f16(tmem_base, a_desc + uint64_t(kk * 2), b_desc + uint64_t(kk * 2), idesc, uint32_t((s | kk) != 0));
+        umma_commit(bar_empty + stage * 8);
+      }
+      __syncwarp();
+      if (++stage == nst) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+    if (leader) umma_commit(bar_acc);
+    __syncwarp();
+  } else {
+    // epilogue: thread = output feature (TMEM lane); 64 token columns
+    const int quarter = warp & 3;
+    const int f = f0 + quarter * 32 + lane;
+    const float b = p.bias ? p.bias[f] : 0.f;
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < ENC_NT / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c * 32), v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int t = t0 + c * 32 + j;
+        if (t < p.M) {
+          float y = __uint_as_float(v[j]) + b;
+          const size_t o = size_t(t) * p.N + f;   // consecutive lanes -> consecutive features: coalesced
+          if constexpr (EPI == EPI_BIAS_F32) {
+            p.out_f32[o] = y;
+          } else if constexpr (EPI == EPI_BIAS_RES_F32) {
+            p.out_f32[o] = y + p.residual[o];
+          } else if constexpr (EPI == EPI_GELU_BF16) {
+            p.out_bf16[o] = __float2bfloat16_rn(gelu_erf(y));
+          } else {
+            p.out_bf16[o] = __float2bfloat16_rn(quick_gelu(y));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc_cols(tmem_base, ENC_NT);
+}
+
+// ---------------------------------------------------------------------------------------------- row kernels (warp = token)
+template <int H>
+__device__ __forceinline__ void warp_layernorm(const float (&x)[H / 32], const float* __restrict__ g, const float* __restrict__ b,
+                                               float eps, int lane, float (&y)[H / 32]) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < H / 32; ++i) s += x[i];
+  const float mean = warp_allreduce_sum(s) / float(H);
+  float v = 0.f;
+#pragma unroll
+  for (int i = 0; i < H / 32; ++i) {
+    const float d = x[i] - mean;
+    v = fmaf(d, d, v);
+  }
+  const float rstd = rsqrtf(warp_allreduce_sum(v) / float(H) + eps);
+#pragma unroll
+  for (int i = 0; i < H / 32; ++i) {
+    const int c = i * 32 + lane;
+    y[i] = (x[i] - mean) * rstd * g[c] + b[c];
+  }
+}
+
+// BERT embeddings: LN(word[id] + pos[p] + type[tt]) -> fp32 residual stream + bf16 GEMM input.
+// CLIP embeddings (ln_g == nullptr): tok[id] + pos[p] -> fp32 residual stream only.
+template <int H>
+__global__ void embed_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ types, const float* __restrict__ word,
+                             const float* __restrict__ pos, const float* __restrict__ type_emb, const float* __restrict__ ln_g,
+                             const float* __restrict__ ln_b, float eps, int M, int S, float* __restrict__ x_f32,
+                             __nv_bfloat16* __restrict__ x_bf16) {
+  pdl_chain_prologue();
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= M) return;
+  const int id = ids[t], p = t % S, tt = types ? types[t] : 0;
+  float x[H / 32], y[H / 32];
+#pragma unroll
+  for (int i = 0; i < H / 32; ++i) {
+    const int c = i * 32 + lane;
+    x[i] = word[size_t(id) * H + c] + pos[size_t(p) * H + c] + (type_emb ? type_emb[size_t(tt) * H + c] : 0.f);
+  }
+  if (ln_g != nullptr) {
+    warp_layernorm<H>(x, ln_g, ln_b, eps, lane, y);
+  } else {
+#pragma unroll
+    for (int i = 0; i < H / 32; ++i) y[i] = x[i];
+  }
+#pragma unroll
+  for (int i = 0; i < H / 32; ++i) {
+    const int c = i * 32 + lane;
+    x_f32[size_t(t) * H + c] = y[i];
+    if (x_bf16) x_bf16[size_t(t) * H + c] = __float2bfloat16_rn(y[i]);
+  }
+}
+
+// y = LN(x): out_f32 (may alias x, may be null) and / or out_bf16
+template <int H>
+__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b, float eps,
+                                 int M, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+  pdl_chain_prologue();
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= M) return;
+  float v[H / 32], y[H / 32];
+#pragma unroll
+  for (int i = 0; i < H / 32; ++i) v[i] = x[size_t(t) * H + i * 32 + lane];
+  warp_layernorm<H>(v, g, b, eps, lane, y);
+#pragma unroll
+  for (int i = 0; i < H / 32; ++i) {
+    const int c = i * 32 + lane;
+    if (out_f32) out_f32[size_t(t) * H + c] = y[i];
+    if (out_bf16) out_bf16[size_t(t) * H + c] = __float2bfloat16_rn(y[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- attention
+// grid = (heads, B); one CTA = one head of one sequence; K (padded rows) and V of the head in shared memory (fp32);
+// warp w handles query rows w, w + NW, ...: scores over keys (lane = key), softmax with warp reductions, P in shared
+// memory, context with lane = output dim.  mask[b, j] == 0 hides key j (padding); causal hides j > i (CLIP).
+template <int DH>
+__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ mask,
+                                                        __nv_bfloat16* __restrict__ ctx, int S, int H, int causal) {
+  extern __shared__ __align__(16) float att_smem[];
+  pdl_chain_prologue();
+  constexpr int NW = 8;
+  constexpr int KP = DH + 1;              // padded K row: lanes read different rows at the same column
+  constexpr int DPL = DH / 32;            // output dims per lane
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* Ks = att_smem;                   // [S][KP]
+  float* Vs = Ks + size_t(S) * KP;        // [S][DH]
+  float* Ps = Vs + size_t(S) * DH;        // [NW][S]
+  const size_t row0 = size_t(b) * S;
+  const int ld = 3 * H;
+  for (int i = threadIdx.x; i < S * DH; i += blockDim.x) {
+    const int j = i / DH, d = i % DH;
+    const float* src = qkv + (row0 + j) * ld + h * DH + d;
+    Ks[j * KP + d] = src[H];
+    Vs[j * DH + d] = src[2 * H];
+  }
+  __syncthreads();
+  const float scale = rsqrtf(float(DH));
+  float* P = Ps + size_t(warp) * S;
+  for (int i = warp; i < S; i += NW) {
+    float q[DPL];
+#pragma unroll
+    for (int u = 0; u < DPL; ++u) q[u] = qkv[(row0 + i) * ld + h * DH + u * 32 + lane] * scale;
+    const int jend = causal ? i + 1 : S;
+    float mx = -INFINITY;
+    for (int j0 = 0; j0 < jend; j0 += 32) {
+      const int j = j0 + lane;
+      float s = 0.f;
+      const float* kr = Ks + size_t(min(j, S - 1)) * KP;
+#pragma unroll
+      for (int u = 0; u < DPL; ++u)
+#pragma unroll
+        for (int d = 0; d < 32; ++d) s = fmaf(__shfl_sync(0xffffffffu, q[u], d), kr[u * 32 + d], s);
+      const bool ok = j < jend && (mask == nullptr || mask[row0 + j] != 0);
+      s = ok ? s : -INFINITY;
+      if (j < S) P[j] = s;
+      mx = fmaxf(mx, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    __syncwarp();
+    float sum = 0.f;
+    for (int j = lane; j < jend; j += 32) {
+      const float e = (mx == -INFINITY) ? 0.f : __expf(P[j] - mx);
+      P[j] = e;
+      sum += e;
+    }
+    sum = warp_allreduce_sum(sum);
+    __syncwarp();
+    float acc[DPL];
+#pragma unroll
+    for (int u = 0; u < DPL; ++u) acc[u] = 0.f;
+    for (int j = 0; j < jend; ++j) {
+      const float pj = P[j];
+#pragma unroll
+      for (int u = 0; u < DPL; ++u) acc[u] = fmaf(pj, Vs[j * DH + u * 32 + lane], acc[u]);
+    }
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+#pragma unroll
+    for (int u = 0; u < DPL; ++u) ctx[(row0 + i) * H + h * DH + u * 32 + lane] = __float2bfloat16_rn(acc[u] * inv);
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- heads (block = sequence)
+__device__ __forceinline__ float block_sum(float v, float* red) {  // blockDim.x <= 1024, result broadcast
+  v = warp_allreduce_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < int(blockDim.x >> 5); ++w) t += red[w];
+  return t;
+}
+
+// sentence-transformers mean pooling over the attention mask, then L2 normalisation (Normalize module + the reference's
+// own _normalize, app/ml/embeddings.py:46-49: a zero vector stays zero).  blockDim.x == H.
+__global__ void mean_pool_norm_kernel(const float* __restrict__ x, const int32_t* __restrict__ mask, int S, int H,
+                                      float* __restrict__ out) {
+  __shared__ float red[32];
+  pdl_chain_prologue();
+  const int b = blockIdx.x, c = threadIdx.x;
+  float s = 0.f, cnt = 0.f;
+  for (int t = 0; t < S; ++t) {
+    const float m = mask ? float(mask[size_t(b) * S + t] != 0) : 1.f;
+    s = fmaf(m, x[(size_t(b) * S + t) * H + c], s);
+    cnt += m;
+  }
+  const float e = s / fmaxf(cnt, 1e-9f);
+  const float nrm = sqrtf(block_sum(e * e, red));
+  out[size_t(b) * H + c] = nrm > 0.f ? e / nrm : e;
+}
+
+// CLIP text head: hidden state at the EOS position -> final LayerNorm -> text_projection (no bias) -> L2 normalisation.
+// blockDim.x == H == projection dim (512).  eos_id == 2 reproduces the legacy argmax(input_ids) rule of HF's CLIP.
+__global__ void clip_head_kernel(const float* __restrict__ x, const int32_t* __restrict__ ids, int S, int H, int eos_id,
+                                 const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps,
+                                 const float* __restrict__ proj /* [P, H] */, int P, float* __restrict__ out) {
+  extern __shared__ float head_smem[];   // [H] normalised hidden state
+  __shared__ float red[32];
+  __shared__ int s_pos;
+  pdl_chain_prologue();
+  const int b = blockIdx.x, c = threadIdx.x;
+  if (c == 0) {
+    int pos = 0;
+    if (eos_id == 2) {
+      int best = ids[size_t(b) * S];
+      for (int t = 1; t < S; ++t)
+        if (ids[size_t(b) * S + t] > best) {
+          best = ids[size_t(b) * S + t];
+          pos = t;
+        }
+    } else {
+      for (int t = 0; t < S; ++t)
+        if (ids[size_t(b) * S + t] == eos_id) {
+          pos = t;
+          break;
+        }
+    }
+    s_pos = pos;
+  }
+  __syncthreads();
+  const float v = x[(size_t(b) * S + s_pos) * H + c];
+  const float mean = block_sum(v, red) / float(H);
+  const float d = v - mean;
+  const float rstd = rsqrtf(block_sum(d * d, red) / float(H) + eps);
+  head_smem[c] = d * rstd * ln_g[c] + ln_b[c];
+  __syncthreads();
+  float e = 0.f;
+  if (c < P) {
+    const float* w = proj + size_t(c) * H;
+    for (int i = 0; i < H; ++i) e = fmaf(w[i], head_smem[i], e);
+  }
+  const float nrm = sqrtf(block_sum(c < P ? e * e : 0.f, red));
+  if (c < P) out[size_t(b) * P + c] = nrm > 0.f ? e / nrm : e;
+}
+
+// Cross-encoder head (BertForSequenceClassification, one label): logit = w_c . tanh(W_p h_CLS + b_p) + b_c.  blockDim.x == H.
+__global__ void cross_head_kernel(const float* __restrict__ x, int S, int H, const float* __restrict__ pool_w,
+                                  const float* __restrict__ pool_b, const float* __restrict__ cls_w,
+                                  const float* __restrict__ cls_b, float* __restrict__ out) {
+  extern __shared__ float head_smem[];   // [H] CLS hidden state
+  __shared__ float red[32];
+  pdl_chain_prologue();
+  const int b = blockIdx.x, c = threadIdx.x;
+  head_smem[c] = x[(size_t(b) * S) * H + c];
+  __syncthreads();
+  const float* w = pool_w + size_t(c) * H;
+  float e = pool_b[c];
+  for (int i = 0; i < H; ++i) e = fmaf(w[i], head_smem[i], e);
+  const float logit = block_sum(tanhf(e) * cls_w[c], red);
+  if (c == 0) out[b] = logit + cls_b[0];
+}
+
+// fp32 -> bf16 weight conversion (set_weight)
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    dst[i] = __float2bfloat16_rn(src[i]);
+}
+#endif  // __CUDACC__
+
+}  // namespace mmr

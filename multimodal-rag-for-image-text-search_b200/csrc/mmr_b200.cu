@@ -1,6 +1,6 @@
 // libmmr_b200.so -- C ABI (include/mmr_b200.h) over the sm_100a scan kernels.
 // Host side: argument checks, planning (which kernel, grid, workspace carve-up), launches.
-#include "../../include/mmr_b200.h"
+#include "abi_common.h"
 
 #include <algorithm>
 #include <atomic>
@@ -29,25 +29,22 @@
 using namespace mmr;
 
 // ------------------------------------------------------------------------------------------------ errors
-static thread_local std::string g_err;
+thread_local std::string mmr_g_err;
+std::atomic<int64_t> mmr_g_launches{0};
 static thread_local int g_last_kernel = 0;
-static std::atomic<int64_t> g_launches{0};
+#define g_err mmr_g_err
+#define g_launches mmr_g_launches
+#define fail mmr_fail
 
-static int fail(int code, const char* fmt, ...) {
+int mmr_fail(int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(buf, sizeof(buf), fmt, ap);
   va_end(ap);
-  g_err = buf;
+  mmr_g_err = buf;
   return code;
 }
-#define CUDA_TRY(expr)                                                                                \
-  do {                                                                                                \
-    cudaError_t e_ = (expr);                                                                          \
-    if (e_ != cudaSuccess) return fail(MMR_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
-                                       __FILE__, __LINE__);                                           \
-  } while (0)
 
 // ------------------------------------------------------------------------------------------------ index
 struct mmr_index {
@@ -104,6 +101,8 @@ static int* option_slot(const char* name) {
   if (!strcmp(name, "MMR_UMMA_NOPROBE")) return &o.umma_noprobe;
   if (!strcmp(name, "MMR_FORCE_FAMILY")) return &o.force_family;
   if (!strcmp(name, "MMR_UMMA_QUAD")) return &o.umma_quad;
+  if (!strcmp(name, "MMR_INLINE_QUERY")) return &o.inline_query;
+  if (!strcmp(name, "MMR_MAILBOX")) return &o.mailbox;
   return nullptr;
 }
 static int parse_option(const char* name, const char* v, int dflt) {
@@ -112,7 +111,7 @@ static int parse_option(const char* name, const char* v, int dflt) {
   return atoi(v);
 }
 static const char* kOptionNames[] = {"MMR_PDL", "MMR_UMMA_MODE", "MMR_UMMA_PAIR", "MMR_UMMA_NOPROBE", "MMR_FORCE_FAMILY",
-                                     "MMR_UMMA_QUAD"};
+                                     "MMR_UMMA_QUAD", "MMR_INLINE_QUERY", "MMR_MAILBOX"};
 namespace {
 struct OptionsFromEnv {  // the environment is read once, when the library is loaded
   OptionsFromEnv() {
@@ -473,7 +472,9 @@ struct Completion {  // optional mailbox flag (mapped host memory) released by t
 
 static int k1_group(const mmr_index* ix) { return ix->dtype == MMR_F32 ? 8 : 4; }  // queries per pass
 
-static bool can_inline(const mmr_index* ix, int B) { return B * ix->dim <= K1_INLINE_FLOATS && B <= 2; }
+static bool can_inline(const mmr_index* ix, int B) {
+  return options().inline_query && B * ix->dim <= K1_INLINE_FLOATS && B <= 2;
+}
 
 static int search_uniform_stream(const mmr_index* ix, QuerySrc q, int B, int k, uint32_t r0, uint32_t r1,
                                  float* out_s, int64_t* out_r, uint8_t* ws, cudaStream_t st,
@@ -512,7 +513,7 @@ static int search_uniform_stream(const mmr_index* ix, QuerySrc q, int B, int k, 
           p.peer_flag[g] = xi->flag[g];
         }
       }
-      if (done && done->flag_dev) {
+      if (done && done->flag_dev && options().mailbox) {
         p.done_flag = done->flag_dev;
         p.done_seq = done->seq;
         done->armed = true;
@@ -935,7 +936,7 @@ static int exchange_impl(const mmr_index* ix, QuerySrc q, int B, int k, bool uni
   cfg.numAttrs = 1;
   uint32_t* done_flag = nullptr;
   uint32_t done_seq = 0;
-  if (done && done->flag_dev && cfg.gridDim.x == 1) {  // one block writes every result: it can ring the mailbox itself
+  if (done && done->flag_dev && cfg.gridDim.x == 1 && options().mailbox) {  // one block writes every result: it rings the mailbox
     done_flag = done->flag_dev;
     done_seq = done->seq;
     done->armed = true;

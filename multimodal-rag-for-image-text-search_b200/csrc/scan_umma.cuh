@@ -132,7 +132,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_m128_n128(bool bf16) {
 // memory, unsorted) by overwriting the current minimum, and return the new minimum = the thread's k-th best key
 // (0 while fewer than k candidates are held).  Replace-min keeps the loads independent (no shifting chain);
 // merge_partials_kernel does the final ordering.  *meta = held count | position of the minimum << 8.
-__device__ __noinline__ uint64_t k2_list_insert(uint64_t* mine, uint32_t* meta, int k, uint64_t key) {
+static __device__ __noinline__ uint64_t k2_list_insert(uint64_t* mine, uint32_t* meta, int k, uint64_t key) {
   const uint32_t m = *meta;
   int count = int(m & 0xffu);
   if (count < k) {

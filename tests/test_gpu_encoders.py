@@ -1,0 +1,154 @@
+"""Device encoders against plain fp32 PyTorch on the SAME weights.
+
+The HF modules are built from their configs with seeded random weights (no checkpoint files offline); the linear weights
+are rounded to bf16-representable values first, so both sides hold identical weights and only the activation precision
+differs (bf16 GEMM inputs on the device, fp32 in torch).  Tolerance: |delta| <= 1e-3 per component of
+the unit-norm embedding; 2e-3 on the cross-encoder logit."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+PKG = "multimodal-rag-for-image-text-search_b200"
+TOL = 1e-3
+
+
+def _round_linear_weights(model):
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if p.dim() == 2 and "embedding" not in name.lower():
+                p.copy_(p.to(torch.bfloat16).to(torch.float32))
+    return model.eval()
+
+
+def _spread(model, scale=2.0):
+    """Random init (std 0.02) gives near-uniform attention; scale the projections up so softmax / GELU / LN see spread."""
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if p.dim() == 2 and "embedding" not in name.lower():
+                p.mul_(scale)
+            elif p.dim() == 1 and "bias" in name:
+                p.normal_(0.0, 0.05)
+            elif p.dim() == 1 and "weight" in name:
+                p.normal_(1.0, 0.1)
+    return model
+
+
+@pytest.fixture(scope="module")
+def enc_mod():
+    return importlib.import_module(PKG + ".encoders")
+
+
+@pytest.fixture(scope="module")
+def bert():
+    from transformers import BertConfig, BertModel
+    torch.manual_seed(0)
+    cfg = BertConfig(vocab_size=30522, hidden_size=384, num_hidden_layers=6, num_attention_heads=12, intermediate_size=1536,
+                     max_position_embeddings=512)
+    return _round_linear_weights(_spread(BertModel(cfg, add_pooling_layer=False)))
+
+
+def _bert_reference(model, ids, mask, types=None):
+    with torch.no_grad():
+        h = model(input_ids=ids, attention_mask=mask, token_type_ids=types).last_hidden_state
+        m = mask[..., None].float()
+        e = (h * m).sum(1) / m.sum(1).clamp(min=1e-9)          # sentence-transformers mean pooling
+        return torch.nn.functional.normalize(e, dim=1)         # Normalize module + the reference's _normalize
+
+
+@pytest.mark.parametrize("b,s", [(1, 12), (5, 40), (33, 7), (2, 130), (128, 16)])
+def test_minilm_text_encoder_matches_fp32_torch(enc_mod, bert, b, s):
+    g = torch.Generator().manual_seed(b * 1000 + s)
+    ids = torch.randint(1000, 30000, (b, s), generator=g)
+    lens = torch.randint(max(1, s // 3), s + 1, (b,), generator=g)
+    lens[0] = s
+    mask = (torch.arange(s)[None, :] < lens[:, None]).long()
+    enc = enc_mod.DeviceEncoder.from_hf_bert(bert)
+    assert enc.kind == "minilm" and enc.out_dim == 384
+    got = enc.forward_ids(ids.numpy(), mask.numpy()).cpu()
+    want = _bert_reference(bert, ids, mask)
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() <= TOL, (got - want).abs().max().item()
+    assert torch.allclose(got.norm(dim=1), torch.ones(b), atol=1e-5)
+    # mask = None means "no padding"
+    got2 = enc.forward_ids(ids.numpy()).cpu()
+    assert (got2 - _bert_reference(bert, ids, torch.ones_like(ids))).abs().max().item() <= TOL
+    enc.close()
+
+
+def test_clip_text_tower_matches_fp32_torch(enc_mod):
+    from transformers import CLIPTextConfig, CLIPTextModelWithProjection
+    torch.manual_seed(1)
+    model = _round_linear_weights(_spread(CLIPTextModelWithProjection(CLIPTextConfig()), 2.0))
+    enc = enc_mod.DeviceEncoder.from_hf_clip(model)
+    assert enc.kind == "clip_text" and enc.out_dim == 512
+    for b, s in ((1, 9), (6, 25), (40, 77)):
+        g = torch.Generator().manual_seed(s)
+        ids = torch.randint(1000, 40000, (b, s), generator=g)
+        ids[:, 0] = 49406
+        lens = torch.randint(3, s + 1, (b,), generator=g)
+        lens[0] = s
+        mask = (torch.arange(s)[None, :] < lens[:, None]).long()
+        for i in range(b):                                   # EOS closes every sequence, padding repeats it (CLIP tokenizer)
+            ids[i, lens[i] - 1:] = 49407
+        with torch.no_grad():
+            want = torch.nn.functional.normalize(model(input_ids=ids, attention_mask=mask).text_embeds, dim=1)
+        got = enc.forward_ids(ids.numpy(), mask.numpy()).cpu()
+        assert (got - want).abs().max().item() <= TOL, (b, s, (got - want).abs().max().item())
+    enc.close()
+
+
+def test_cross_encoder_logits_match_fp32_torch(enc_mod):
+    from transformers import BertConfig, BertForSequenceClassification
+    torch.manual_seed(2)
+    cfg = BertConfig(vocab_size=30522, hidden_size=384, num_hidden_layers=6, num_attention_heads=12, intermediate_size=1536,
+                     max_position_embeddings=512, num_labels=1)
+    model = _round_linear_weights(_spread(BertForSequenceClassification(cfg)))
+    enc = enc_mod.DeviceEncoder.from_hf_bert(model)
+    assert enc.kind == "cross" and enc.out_dim == 1
+    for b, s in ((8, 64), (3, 300), (16, 128)):
+        g = torch.Generator().manual_seed(s)
+        ids = torch.randint(1000, 30000, (b, s), generator=g)
+        lens = torch.randint(s // 2, s + 1, (b,), generator=g)
+        mask = (torch.arange(s)[None, :] < lens[:, None]).long()
+        types = (torch.arange(s)[None, :] >= (lens[:, None] // 3)).long() * mask      # query segment 0, passage segment 1
+        with torch.no_grad():
+            want = model(input_ids=ids, attention_mask=mask, token_type_ids=types).logits[:, 0]
+        got = enc.forward_ids(ids.numpy(), mask.numpy(), types.numpy()).cpu()
+        assert got.shape == (b,)
+        assert (got - want).abs().max().item() <= 2e-3, (b, s, (got - want).abs().max().item(), want[:4], got[:4])
+    enc.close()
+
+
+def test_query_is_born_on_the_device_and_feeds_the_scan(enc_mod, bert):
+    """embed -> search without a host hop: the encoder's output tensor IS mmr_search's query buffer."""
+    from tests import util
+    mmr = importlib.import_module(PKG)
+    rows = util.unit_rows(50_000, 384, seed=5)
+    ix = mmr.ResidentIndex.from_f32(rows, dtype="bf16")
+    enc = enc_mod.DeviceEncoder.from_hf_bert(bert)
+
+    class Tok:  # a stand-in tokenizer (the real one needs vocab files): hashes words to ids
+        def __call__(self, texts, padding=True, truncation=True, return_tensors="np", max_length=256):
+            toks = [[101] + [1000 + (hash(w) % 20000) for w in t.split()][: max_length - 2] + [102] for t in texts]
+            s = max(len(t) for t in toks)
+            ids = np.zeros((len(toks), s), np.int64)
+            mask = np.zeros((len(toks), s), np.int64)
+            for i, t in enumerate(toks):
+                ids[i, : len(t)], mask[i, : len(t)] = t, 1
+            return {"input_ids": ids, "attention_mask": mask, "token_type_ids": np.zeros_like(ids)}
+
+    text_enc = enc_mod.TextQueryEncoder(Tok(), enc)
+    q_dev = text_enc.encode_device(["what is in the picture", "a much longer question about retrieval augmented generation"])
+    assert q_dev.is_cuda and q_dev.shape == (2, 384)
+    s, r = ix.search(q_dev, 10)
+    host = text_enc(["what is in the picture", "a much longer question about retrieval augmented generation"])
+    s2, r2 = ix.search_host(host, 10)
+    assert (r.cpu().numpy() == r2).all()
+    for j in range(2):
+        util.check_topk(s[j].cpu().numpy(), r[j].cpu().numpy(), util.oracle_scores(rows, host[j]), 10, util.TOL_BF16, what="enc->scan")
+    assert text_enc([]).shape == (0, 384)
+    enc.close()
+    ix.close()

@@ -50,11 +50,11 @@ def test_fuzz_against_oracle(seed):
             segs = "ranges"                                                # explicit multi-range queries
             ranges = []
             for _ in range(b):
-                rr = []
-                for _ in range(int(rng.integers(0, 4))):
-                    lo = int(rng.integers(0, n))
-                    rr.append((lo, int(rng.integers(lo, n + 1))))
-                ranges.append(rr)
+                nr = int(rng.integers(0, 4))                   # 0..3 disjoint ranges (overlaps are rejected by the ABI)
+                cuts = np.sort(rng.integers(0, n + 1, size=2 * nr))
+                rr = [(int(cuts[2 * i]), int(cuts[2 * i + 1])) for i in range(nr)]
+                rng.shuffle(rr)                                 # any order
+                ranges.append([tuple(x) for x in rr])
         qd = torch.from_numpy(q).cuda()
         if segs == "ranges":
             s, r = ix.search_ranges(qd, k, ranges)
