@@ -82,7 +82,7 @@ __global__ void merge_shards_kernel(const float* __restrict__ scores, const int6
       valid = r >= 0;
       if (valid) key = make_key(scores[size_t(g) * score_stride + o], uint32_t(r));
     }
-    thr = m.offer(key, valid, thr, k, lane);
+    thr = m.offer_batch(key, valid, thr, k, lane);
   }
 #pragma unroll
   for (int j = 0; j < KPL; ++j) {
@@ -209,7 +209,7 @@ __device__ __forceinline__ void merge_wait_body(const uint8_t* __restrict__ xbuf
       valid = r >= 0;
       if (valid) key = make_key(__ldcg(reinterpret_cast<const float*>(slot) + o), uint32_t(r));
     }
-    thr = m.offer(key, valid, thr, k, lane);
+    thr = m.offer_batch(key, valid, thr, k, lane);
   }
 #pragma unroll
   for (int j = 0; j < KPL; ++j) {

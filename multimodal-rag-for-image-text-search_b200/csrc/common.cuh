@@ -53,7 +53,8 @@ struct Options {
   int force_family = 0;   // MMR_FORCE_FAMILY 1 = K1, 2 = K2 regardless of batch size
   int umma_quad = 1;      // MMR_UMMA_QUAD=0  no 4-CTA multicast clusters
   int inline_query = 1;   // MMR_INLINE_QUERY=0  host-buffer calls always stage the query with an H2D copy (measurement)
-  int mailbox = 1;        // MMR_MAILBOX=0       host-buffer calls synchronise the stream instead of spinning on the flag
+  int mailbox = 0;        // MMR_MAILBOX=1       host-buffer calls spin on a flag the kernel writes into the mapped mailbox instead
+                          //                     of synchronising the stream (measured no faster: profiles/r02_fixed_cost.json)
 };
 inline Options& options() {
   static Options o;
@@ -67,6 +68,11 @@ inline Options& options() {
 __device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
   uint32_t lo = __shfl_sync(0xffffffffu, uint32_t(v), src);
   uint32_t hi = __shfl_sync(0xffffffffu, uint32_t(v >> 32), src);
+  return (uint64_t(hi) << 32) | lo;
+}
+__device__ __forceinline__ uint64_t shfl_u64_xor(uint64_t v, int mask) {
+  uint32_t lo = __shfl_xor_sync(0xffffffffu, uint32_t(v), mask);
+  uint32_t hi = __shfl_xor_sync(0xffffffffu, uint32_t(v >> 32), mask);
   return (uint64_t(hi) << 32) | lo;
 }
 __device__ __forceinline__ uint64_t shfl_up_u64(uint64_t v, int d) {

@@ -488,7 +488,7 @@ __global__ void probe_floor_kernel(const float* __restrict__ probe, int n_qtiles
     const int rs = i0 + lane;
     const bool valid = rs < n_rslots;
     const float v = valid ? probe[size_t(qt * n_rslots + rs) * K2_BM + ql] : -INFINITY;
-    thr = m.offer(make_key(v, uint32_t(rs)), valid && v > -INFINITY, thr, k, lane);
+    thr = m.offer_batch(make_key(v, uint32_t(rs)), valid && v > -INFINITY, thr, k, lane);
   }
   if (lane == 0) floor[q] = thr ? key_score(thr) : -INFINITY;
 }

@@ -225,9 +225,15 @@ class ResidentIndex:
         scores = np.empty((b, k), dtype=np.float32)
         rows = np.empty((b, k), dtype=np.int64)
         seg_arr = None if segments is None else np.ascontiguousarray(segments, dtype=np.int32)
-        with torch.cuda.device(self.device):
+        # (the C call selects the index's device itself; entering torch's device context costs ~10 us per request, so it
+        #  is only done when another device is current)
+        if torch.cuda.current_device() == (self.device.index or 0):
             N.check(N.lib().mmr_search_host(self._handle, q.ctypes.data, None if seg_arr is None else seg_arr.ctypes.data,
                                             b, k, scores.ctypes.data, rows.ctypes.data, _stream_ptr(self.device)))
+        else:
+            with torch.cuda.device(self.device):
+                N.check(N.lib().mmr_search_host(self._handle, q.ctypes.data, None if seg_arr is None else seg_arr.ctypes.data,
+                                                b, k, scores.ctypes.data, rows.ctypes.data, _stream_ptr(self.device)))
         return scores, rows
 
 

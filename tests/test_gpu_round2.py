@@ -131,14 +131,19 @@ def test_host_calls_mailbox_and_reentrancy(mmr, table):
     lib = mmr._native.lib()
     q = util.queries(6, 512, seed=311)
     qd = torch.from_numpy(q).cuda()
-    for b, segs in ((1, [4]), (2, [4, 4]), (2, None), (5, [4] * 5), (6, [0, 2, 4, 5, 2, -1]), (1, [1])):
-        n0 = lib.mmr_launch_count()
-        hs, hr = ix.search_host(q[:b], 10, segs)
-        launches = lib.mmr_launch_count() - n0
-        ds, dr = ix.search(qd[:b], 10, segs)
-        assert (hr == dr.cpu().numpy()).all() and (hs == ds.cpu().numpy()).all(), (b, segs)
-        if b <= 2:
-            assert launches == 1, "the single-request path is one kernel launch"
+    for mailbox, inline in (("0", "1"), ("1", "1"), ("1", "0")):   # completion by stream sync / by the kernel-written flag
+        mmr._native.set_option("MMR_MAILBOX", mailbox)
+        mmr._native.set_option("MMR_INLINE_QUERY", inline)
+        for b, segs in ((1, [4]), (2, [4, 4]), (2, None), (5, [4] * 5), (6, [0, 2, 4, 5, 2, -1]), (1, [1])):
+            n0 = lib.mmr_launch_count()
+            hs, hr = ix.search_host(q[:b], 10, segs)
+            launches = lib.mmr_launch_count() - n0
+            ds, dr = ix.search(qd[:b], 10, segs)
+            assert (hr == dr.cpu().numpy()).all() and (hs == ds.cpu().numpy()).all(), (b, segs, mailbox, inline)
+            if b <= 2:
+                assert launches == 1, "the single-request path is one kernel launch"
+    mmr._native.set_option("MMR_MAILBOX", None)
+    mmr._native.set_option("MMR_INLINE_QUERY", None)
     errors = []
 
     def worker(j):
