@@ -58,7 +58,7 @@ typedef struct mmr_index mmr_index;
 /* Library / error plumbing. */
 int mmr_abi_version(void);
 const char* mmr_last_error(void);
-/* Switches (MMR_PDL, MMR_UMMA_MODE, MMR_UMMA_PAIR, MMR_UMMA_NOPROBE, MMR_FORCE_FAMILY, MMR_UMMA_QUAD).  The
+/* Switches (MMR_PDL, MMR_UMMA_MODE, MMR_UMMA_PAIR, MMR_UMMA_NOPROBE, MMR_FORCE_FAMILY, MMR_UMMA_LOCKSTEP).  The
  * environment is read once when the library is loaded; these change / read a switch afterwards (value NULL or "" =
  * default).  mmr_get_option returns -1 for an unknown name. */
 int mmr_set_option(const char* name, const char* value);

@@ -100,7 +100,7 @@ static int* option_slot(const char* name) {
   if (!strcmp(name, "MMR_UMMA_PAIR")) return &o.umma_pair;
   if (!strcmp(name, "MMR_UMMA_NOPROBE")) return &o.umma_noprobe;
   if (!strcmp(name, "MMR_FORCE_FAMILY")) return &o.force_family;
-  if (!strcmp(name, "MMR_UMMA_QUAD")) return &o.umma_quad;
+  if (!strcmp(name, "MMR_UMMA_LOCKSTEP")) return &o.umma_lockstep;
   if (!strcmp(name, "MMR_INLINE_QUERY")) return &o.inline_query;
   if (!strcmp(name, "MMR_MAILBOX")) return &o.mailbox;
   return nullptr;
@@ -111,7 +111,7 @@ static int parse_option(const char* name, const char* v, int dflt) {
   return atoi(v);
 }
 static const char* kOptionNames[] = {"MMR_PDL", "MMR_UMMA_MODE", "MMR_UMMA_PAIR", "MMR_UMMA_NOPROBE", "MMR_FORCE_FAMILY",
-                                     "MMR_UMMA_QUAD", "MMR_INLINE_QUERY", "MMR_MAILBOX"};
+                                     "MMR_UMMA_LOCKSTEP", "MMR_INLINE_QUERY", "MMR_MAILBOX"};
 namespace {
 struct OptionsFromEnv {  // the environment is read once, when the library is loaded
   OptionsFromEnv() {

@@ -54,6 +54,11 @@ struct UmmaParams {
   uint32_t idesc;       // tcgen05 instruction descriptor (bf16 or fp16 operands)
   float* dump;        // DUMP mode: raw scores [B][dump_ld]
   int64_t dump_ld;
+  // Lockstep window (pair mode, >= 2 query pairs per row slot): progress[rs * n_qpairs + qpair] = tiles started by that
+  // pair; a pair that runs more than `window` tiles ahead of the slowest pair of its row slot waits.  Keeps the pairs that
+  // read the same index tiles within an L2-resident window, so each tile is fetched from HBM once (it was 1.5-2x).
+  uint32_t* progress;
+  int32_t window;
 };
 
 #ifdef __CUDACC__
@@ -560,11 +565,13 @@ inline size_t umma_align(size_t v) { return (v + 255) / 256 * 256; }
 
 inline int umma_qtiles(int B) { return (B + K2_BM - 1) / K2_BM; }
 
+constexpr size_t K2_PROGRESS_BYTES = 4096;  // lockstep counters: one u32 per CTA pair
+
 inline size_t umma_workspace_bytes(int sm_count, int dim, int B, int k) {
   const int qtiles = std::min(umma_qtiles(B), sm_count);
   const int ctas = std::max(sm_count, qtiles);
   return umma_align(size_t(B) * dim * 2) + umma_align(size_t(ctas) * K2_BM * k * 8) +
-         umma_align(size_t(ctas) * K2_BM * 4) + umma_align(size_t(B) * 4) + 256;
+         umma_align(size_t(ctas) * K2_BM * 4) + umma_align(size_t(B) * 4) + K2_PROGRESS_BYTES + 256;
 }
 
 inline int umma_launches_per_search() { return 5; }  // prep, probe, floor, scan, merge

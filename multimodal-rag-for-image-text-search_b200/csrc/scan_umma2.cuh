@@ -143,7 +143,20 @@ scan_umma2_kernel(const __grid_constant__ CUtensorMap tm_x, const UmmaParams p) 
     const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
+    // lockstep with the other pairs of this row slot (they stream the same index tiles): see UmmaParams::progress
+    const bool lockstep = p.progress != nullptr && p.probe_out == nullptr && lead_cta && n_qpairs > 1;
+    volatile uint32_t* prog = lockstep ? p.progress + size_t(rs) * n_qpairs : nullptr;
+    uint32_t started = 0;
     for (int t = rs; t < ntiles; t += p.n_rslots) {
+      if (lockstep && (started & 3u) == 0u) {
+        if (leader) {
+          prog[qpair] = started;
+          for (int qp = 0; qp < n_qpairs; ++qp)
+            while (prog[qp] + uint32_t(p.window) < started) __nanosleep(100);
+        }
+        __syncwarp();
+      }
+      ++started;
       const int32_t row0 = int32_t(p.row_begin + uint32_t(t) * K2_NT + rank * K2X_HALF);
       for (int s = 0; s < ks; ++s) {
         mbar_wait(bar_empty + stage * 8, phase ^ 1u);
@@ -158,6 +171,7 @@ scan_umma2_kernel(const __grid_constant__ CUtensorMap tm_x, const UmmaParams p) 
         }
       }
     }
+    if (lockstep && leader) prog[qpair] = 0xFFFFFFFFu - uint32_t(p.window);   // done: nobody waits for this pair any more
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (lead_cta) {
@@ -408,6 +422,7 @@ inline int umma_search(UmmaIndexState& st, Umma2IndexState& st2, const void* row
   const int ctas_max = std::max(sm_count, std::min(umma_qtiles(B), sm_count));
   float* probe = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(partial) + umma_align(size_t(ctas_max) * K2_BM * k * 8));
   float* floor = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(probe) + umma_align(size_t(ctas_max) * K2_BM * 4));
+  uint32_t* progress = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(floor) + umma_align(size_t(B) * 4));
   const bool noprobe = options().umma_noprobe != 0;
   if (dtype == MMR_BF16) launch_pdl(prep_queries_kernel<__nv_bfloat16>, dim3((B + 3) / 4), dim3(128), 0, stream, queries, qb, B, dim);
   else launch_pdl(prep_queries_kernel<__half>, dim3((B + 3) / 4), dim3(128), 0, stream, queries, reinterpret_cast<__half*>(qb), B, dim);
@@ -465,6 +480,13 @@ inline int umma_search(UmmaIndexState& st, Umma2IndexState& st2, const void* row
       if (k <= 32) launch_pdl(probe_floor_kernel<1>, dim3((bq + wpb - 1) / wpb), dim3(wpb * 32), 0, stream, probe, p.n_qtiles, p.n_rslots, bq, k, floor + q0);
       else launch_pdl(probe_floor_kernel<2>, dim3((bq + wpb - 1) / wpb), dim3(wpb * 32), 0, stream, probe, p.n_qtiles, p.n_rslots, bq, k, floor + q0);
       p.floor = floor + q0;
+    }
+    if (pair && n_qpairs > 1 && options().umma_lockstep && grid <= sm_count &&
+        size_t(p.n_rslots) * n_qpairs * 4 <= K2_PROGRESS_BYTES) {  // every CTA must be resident: waiting pairs spin
+      // (MMR_UMMA_LOCKSTEP=0 switches the lockstep window off: measurement)
+      cudaMemsetAsync(progress, 0, size_t(p.n_rslots) * n_qpairs * 4, stream);
+      p.progress = progress;
+      p.window = 24;   // tiles: 24 x 128 KB x row slots stays far inside the 126 MB L2
     }
     if (dump) {
       if (pair) launch_pdl(scan_umma2_kernel<true>, dim3(grid), dim3(K2_THREADS), smem2_bytes, stream, st2.map, p);

@@ -49,7 +49,7 @@ class ResidentIndex:
         self.seg_offsets = None if seg_offsets is None else np.ascontiguousarray(seg_offsets, dtype=np.int64)
         self._handle = C.c_void_p()
         self._ws: Optional[torch.Tensor] = None
-        self._ws_key = (0, 0)
+        self._ws_key = (0, 0, 0)
         lib = N.lib()
         nseg = 0 if self.seg_offsets is None else len(self.seg_offsets) - 1
         segp = None if self.seg_offsets is None else self.seg_offsets.ctypes.data
@@ -163,11 +163,14 @@ class ResidentIndex:
 
     # -- search ---------------------------------------------------------------------------------
     def _workspace(self, b: int, k: int, n_ranges: int = 0) -> torch.Tensor:
-        lib = N.lib()
-        need = max(lib.mmr_search_workspace_bytes(self._handle, b, k),
-                   lib.mmr_search_ranges_workspace_bytes(self._handle, b, k, n_ranges) if n_ranges else 0)
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.zeros(int(need), dtype=torch.uint8, device=self.device)
+        key = (b, k, n_ranges)
+        if key != self._ws_key or self._ws is None:
+            lib = N.lib()
+            need = max(lib.mmr_search_workspace_bytes(self._handle, b, k),
+                       lib.mmr_search_ranges_workspace_bytes(self._handle, b, k, n_ranges) if n_ranges else 0)
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.zeros(int(need), dtype=torch.uint8, device=self.device)
+            self._ws_key = key
         return self._ws
 
     def set_query_precision(self, mode: str) -> None:
@@ -197,10 +200,13 @@ class ResidentIndex:
             if seg_arr.shape != (b,):
                 raise ValueError("segments must have one entry per query")
         ws = self._workspace(b, k)
-        with torch.cuda.device(self.device):
-            N.check(N.lib().mmr_search(self._handle, queries.data_ptr(), None if seg_arr is None else seg_arr.ctypes.data,
-                                       b, k, scores.data_ptr(), rows.data_ptr(), ws.data_ptr(), ws.numel(),
-                                       _stream_ptr(self.device)))
+        args = (self._handle, queries.data_ptr(), None if seg_arr is None else seg_arr.ctypes.data, b, k, scores.data_ptr(),
+                rows.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(self.device))
+        if torch.cuda.current_device() == (self.device.index or 0):   # (entering torch's device context costs ~10 us)
+            N.check(N.lib().mmr_search(*args))
+        else:
+            with torch.cuda.device(self.device):
+                N.check(N.lib().mmr_search(*args))
         return scores, rows
 
     def debug_umma_scores(self, queries: torch.Tensor, row_begin: int, row_end: int) -> torch.Tensor:

@@ -163,7 +163,7 @@ class ShardedIndex:
         rows = np.empty((b, k), dtype=np.int64)
         seg_arr = None if segments is None else np.ascontiguousarray(segments, dtype=np.int32)
         peer.seq += 1
-        with torch.cuda.device(ix.device):
+        if True:   # (the C call selects the device itself)
             N.check(N.lib().mmr_search_exchange_host(ix._handle, q.ctypes.data, None if seg_arr is None else seg_arr.ctypes.data,
                                                      b, k, peer.ptrs.ctypes.data, self.world, self.rank, peer.seq,
                                                      scores.ctypes.data, rows.ctypes.data, _stream_ptr(ix.device)))
