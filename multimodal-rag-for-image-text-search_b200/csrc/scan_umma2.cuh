@@ -108,6 +108,7 @@ scan_umma2_kernel(const __grid_constant__ CUtensorMap tm_x, const UmmaParams p) 
   const uint32_t bar_tempty = bar_tfull + K2X_ACC * 8;            // [K2X_ACC]         used in the leader
   const uint32_t bar_q = bar_tempty + K2X_ACC * 8;                // [1]               used in the leader
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * K2X_MAX_STAGES + 2 * K2X_ACC + 1);
+  uint32_t* pace = tmem_slot + 2;   // [0] tiles started by this CTA's producer, [1] tiles it may start (lockstep window)
 
   const int pair = int(blockIdx.x >> 1);
   const int n_qpairs = (p.n_qtiles + 1) >> 1;
@@ -118,7 +119,11 @@ scan_umma2_kernel(const __grid_constant__ CUtensorMap tm_x, const UmmaParams p) 
   const int ntiles_all = int((nrows + K2_NT - 1) / K2_NT);
   const int ntiles = p.probe_out ? min(ntiles_all, rs + p.probe_tiles * p.n_rslots) : ntiles_all;
 
+  // lockstep (pair mode with several query pairs per row slot): gate = the non-lead CTA's producer, paced by its idle warp 1
+  const bool lockstep = p.progress != nullptr && p.probe_out == nullptr && !lead_cta && n_qpairs > 1;
   if (threadIdx.x == 0) {
+    pace[0] = 0u;
+    pace[1] = uint32_t(p.window);
     if ((st_s & 1023u) != 0) __trap();
     for (int s = 0; s < K2X_MAX_STAGES; ++s) {
       mbar_init(bar_full + s * 8, 1);
@@ -143,16 +148,15 @@ scan_umma2_kernel(const __grid_constant__ CUtensorMap tm_x, const UmmaParams p) 
     const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
-    // lockstep with the other pairs of this row slot (they stream the same index tiles): see UmmaParams::progress
-    const bool lockstep = p.progress != nullptr && p.probe_out == nullptr && lead_cta && n_qpairs > 1;
-    volatile uint32_t* prog = lockstep ? p.progress + size_t(rs) * n_qpairs : nullptr;
+    // lockstep with the other pairs of this row slot (they stream the same index tiles; see UmmaParams::progress): the
+    // NON-lead CTA's producer is the gate (the pair's MMAs need both halves of a tile), because that CTA's MMA warp is
+    // idle and can do the global polling -- this loop only reads shared memory.
     uint32_t started = 0;
     for (int t = rs; t < ntiles; t += p.n_rslots) {
-      if (lockstep && (started & 3u) == 0u) {
+      if (lockstep) {
         if (leader) {
-          prog[qpair] = started;
-          for (int qp = 0; qp < n_qpairs; ++qp)
-            while (prog[qp] + uint32_t(p.window) < started) __nanosleep(100);
+          while (started >= *reinterpret_cast<volatile uint32_t*>(&pace[1])) __nanosleep(40);
+          *reinterpret_cast<volatile uint32_t*>(&pace[0]) = started + 1;
         }
         __syncwarp();
       }
@@ -171,9 +175,27 @@ scan_umma2_kernel(const __grid_constant__ CUtensorMap tm_x, const UmmaParams p) 
         }
       }
     }
-    if (lockstep && leader) prog[qpair] = 0xFFFFFFFFu - uint32_t(p.window);   // done: nobody waits for this pair any more
+    if (lockstep && leader) *reinterpret_cast<volatile uint32_t*>(&pace[0]) = 0xFFFFFFFFu;   // done
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (!lead_cta && lockstep) {
+      // ---------------------------------------------------------------- pacer (this warp has no MMAs to issue)
+      // publishes this pair's progress, polls the other pairs of the row slot, and raises the producer's allowance
+      volatile uint32_t* prog = p.progress + size_t(rs) * n_qpairs;
+      if (lane == 0) {
+        for (;;) {
+          const uint32_t mine = *reinterpret_cast<volatile uint32_t*>(&pace[0]);
+          prog[qpair] = mine;
+          uint32_t slowest = 0xFFFFFFFFu;
+          for (int qp = 0; qp < n_qpairs; ++qp) slowest = min(slowest, prog[qp]);
+          *reinterpret_cast<volatile uint32_t*>(&pace[1]) =
+              slowest > 0xFFFFFFFFu - uint32_t(p.window) ? 0xFFFFFFFFu : slowest + uint32_t(p.window);
+          if (mine == 0xFFFFFFFFu) break;
+          __nanosleep(400);
+        }
+      }
+      __syncwarp();
+    }
     if (lead_cta) {
       const bool leader = elect_one();
       const uint32_t idesc = p.idesc;

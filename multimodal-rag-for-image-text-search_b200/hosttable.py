@@ -96,6 +96,7 @@ class HostTable:
         self.dim: Optional[int] = None
         self.blocks: List[_Block] = []
         self._starts = np.zeros(0, dtype=np.int64)
+        self._starts_list: List[int] = []
         self.n_total = 0
         self.n_alive = 0
         self.alive = np.zeros(0, dtype=bool)
@@ -147,25 +148,26 @@ class HostTable:
 
     def values_at(self, col: str, rows: Sequence[int]) -> list:
         """Column values of several host rows, read straight out of the Arrow buffers (offset pair + one utf-8 decode per
-        value): the metadata side of a hit costs about a microsecond, with no Arrow scalar / compute-kernel round trip."""
-        rows = np.asarray(rows, dtype=np.int64)
-        if rows.size == 0:
-            return []
-        which = np.searchsorted(self._starts, rows, side="right") - 1
-        out = [None] * rows.size
-        for b in (np.unique(which) if (which != which[0]).any() else which[:1]):
-            blk = self.blocks[int(b)]
-            sel = np.nonzero(which == b)[0]
-            local = rows[sel] - blk.start
-            raw = self._raw(blk, col)
+        value): the metadata side of a hit costs about a microsecond, with no Arrow scalar / compute-kernel / numpy
+        small-array round trip (a result list is ~10 rows: plain Python beats vectorisation here)."""
+        import bisect
+
+        out = []
+        starts = self._starts_list
+        single = len(self.blocks) == 1
+        last_b, blk, raw, start = -1, None, None, 0
+        for r in rows:
+            r = int(r)
+            b = 0 if single else bisect.bisect_right(starts, r) - 1
+            if b != last_b:
+                blk = self.blocks[b]
+                raw, start, last_b = self._raw(blk, col), blk.start, b
+            j = r - start
             if raw is None:
-                arr = blk.cols[col]
-                vals = [arr[int(j)].as_py() for j in local]
+                out.append(blk.cols[col][j].as_py())
             else:
                 off, data = raw
-                vals = [str(data[a:e], "utf-8") for a, e in zip(off[local].tolist(), off[local + 1].tolist())]
-            for j, v in zip(sel.tolist(), vals):
-                out[j] = v
+                out.append(str(data[off[j]:off[j + 1]], "utf-8"))
         return out
 
     def gather(self, rows: np.ndarray) -> np.ndarray:
@@ -302,6 +304,7 @@ class HostTable:
             self.alive[killed] = False
         self.blocks.append(_Block(base, n, emb, cols))
         self._starts = np.append(self._starts, base)
+        self._starts_list.append(int(base))
         self.n_total = base + n
         self.n_alive += int(alive_new.sum()) - int(killed.size)
         return base, n, killed, sorted(set(names))

@@ -32,14 +32,31 @@ _METADATA_STORE: Any = None
 _CROSS_ENCODER: Any = None
 embed_text_batch: Optional[Callable[[List[str]], np.ndarray]] = None
 embed_query_for_images: Optional[Callable[[str], np.ndarray]] = None
+# optional device-side models (encoders.TextQueryEncoder / ImageQueryEncoder / DeviceCrossEncoder): when set,
+# retrieve_batch_device embeds the whole micro-batch on the GPU and the embeddings never visit the host
+_DEVICE_TEXT_ENCODER: Any = None
+_DEVICE_IMAGE_ENCODER: Any = None
+_DEVICE_CROSS_ENCODER: Any = None
 
 TEXT_DIM, IMAGE_DIM = 384, 512
 
 
 def configure(store=None, metadata=None, text_encoder=None, image_query_encoder=None, cross_encoder=None,
-              retrieval_settings=None) -> None:
-    """Wire the module-level seams in one call."""
+              retrieval_settings=None, device_text_encoder=None, device_image_encoder=None,
+              device_cross_encoder=None) -> None:
+    """Wire the module-level seams in one call.  A device encoder also serves the matching host seam (it is callable with
+    the reference's signature), so `retrieve()` and `retrieve_batch_device()` use the same model."""
     global _LANCEDB_STORE, _METADATA_STORE, embed_text_batch, embed_query_for_images, _CROSS_ENCODER
+    global _DEVICE_TEXT_ENCODER, _DEVICE_IMAGE_ENCODER, _DEVICE_CROSS_ENCODER
+    if device_text_encoder is not None:
+        _DEVICE_TEXT_ENCODER = device_text_encoder
+        text_encoder = text_encoder or device_text_encoder
+    if device_image_encoder is not None:
+        _DEVICE_IMAGE_ENCODER = device_image_encoder
+        image_query_encoder = image_query_encoder or device_image_encoder
+    if device_cross_encoder is not None:
+        _DEVICE_CROSS_ENCODER = device_cross_encoder
+        cross_encoder = cross_encoder or device_cross_encoder
     if store is not None:
         _LANCEDB_STORE = store
     if metadata is not None:
@@ -116,7 +133,9 @@ def retrieve_text(user_id: str, query: str, top_k: Optional[int] = None) -> List
     vec, _ = _get_embeddings(query)
     if vec.size == 0:
         return []
-    results = _join(_LANCEDB_STORE.search_text(user_id, vec.tolist(), top_k), "text", need_text=True)
+    # (the reference passes vec.tolist(), retrieve.py:53; the store takes any float sequence, and handing it the ndarray
+    #  skips a list round trip of ~40 us per request)
+    results = _join(_LANCEDB_STORE.search_text(user_id, vec, top_k), "text", need_text=True)
     _cache.set_retrieval_results(user_id, key, version, results)
     return results
 
@@ -131,7 +150,7 @@ def retrieve_images(user_id: str, query: str, top_k: Optional[int] = None) -> Li
     _, vec = _get_embeddings(query)
     if vec.size == 0:
         return []
-    results = _join(_LANCEDB_STORE.search_image(user_id, vec.tolist(), top_k), "image", need_text=False)
+    results = _join(_LANCEDB_STORE.search_image(user_id, vec, top_k), "image", need_text=False)
     _cache.set_retrieval_results(user_id, key, version, results)
     return results
 
@@ -149,35 +168,67 @@ def retrieve(user_id: str, query: str) -> List[Dict[str, Any]]:
     return fused
 
 
+def _embed_batch(queries: Sequence[str]):
+    """Query embeddings of a micro-batch: on the device when device encoders are configured (the embeddings are born in
+    HBM and feed the scan directly), else through the host seams of the reference (cached, retrieve.py:120-129)."""
+    if _DEVICE_TEXT_ENCODER is not None and _DEVICE_IMAGE_ENCODER is not None:
+        return _DEVICE_TEXT_ENCODER.encode_device(list(queries)), _DEVICE_IMAGE_ENCODER.encode_device(list(queries))
+    vecs = [_get_embeddings(q) for q in queries]
+    return np.stack([v[0] for v in vecs]), np.stack([v[1] for v in vecs])
+
+
 def retrieve_batch_device(user_ids: Sequence[str], queries: Sequence[str]) -> List[Tuple[List[Dict[str, Any]], bool]]:
     """Micro-batched `retrieve` + `_confidence_low` for B concurrent requests with the fusion and the gate on the
-    device (rerank off).  One launch chain serves the whole batch: text scan, image scan, K5.  Only the FINAL_N winners
-    are joined with the metadata store (<= 4 lookups per request instead of 62).
+    device.  One launch chain serves the whole batch: (query encoders,) text scan, image scan, (cross-encoder,) K5.
+    Only the FINAL_N winners -- plus, with rerank on, the RERANK_TOPK candidates whose text the cross-encoder needs --
+    are joined with the metadata store (<= 12 lookups per request in ONE batched statement instead of 62).
+
+      * RERANK_ENABLED=false (or no reranker): mmr_fuse on the scans' f32 cosines.
+      * rerank on with a device cross-encoder (configure(device_cross_encoder=...)): the (query, passage) pairs of ALL
+        requests share one forward pass, its logits stay on the device and mmr_fuse_f64 reproduces _rerank_text's
+        re-ordering + the rerank z-scores + fusion + gate (reference app/ml/retrieve.py:132-183, generate.py:56-60).
 
     The device fuses every hit the scan returns; the reference fuses the hits that survive the metadata join
     (retrieve.py:57-58,88-89).  Both agree whenever each indexed chunk exists with non-empty text -- which the write
-    path guarantees (index_build.py:52-55 skips empty text).  If a winner nevertheless fails the join, that request
-    is redone through the host path so the reference's semantics are kept."""
+    path guarantees (index_build.py:52-55 skips empty text).  If a candidate or winner nevertheless fails the join, that
+    request is redone through the host path so the reference's semantics are kept."""
     cfg = settings.retrieval
-    if cfg.use_rerank and _get_cross_encoder():
-        raise RuntimeError("retrieve_batch_device serves the rerank-off path (RERANK_ENABLED=false); use retrieve()")
+    rerank_on = bool(cfg.use_rerank and _get_cross_encoder())
+    if rerank_on and _DEVICE_CROSS_ENCODER is None:
+        raise RuntimeError("rerank is on but no device cross-encoder is configured: use retrieve(), or "
+                           "configure(device_cross_encoder=...), or RERANK_ENABLED=false")
     fused_search = getattr(_LANCEDB_STORE, "fused_search_batch", None)
     if fused_search is None:
         raise RuntimeError("the configured store has no device fusion (needs B200Store)")
-    vecs = [_get_embeddings(q) for q in queries]
-    batch = fused_search(user_ids, np.stack([v[0] for v in vecs]), np.stack([v[1] for v in vecs]),
-                         cfg.index_topk_text, cfg.index_topk_image, cfg.final_n, cfg.confidence_tau)
+    text_vecs, image_vecs = _embed_batch(queries)
+    if rerank_on:
+        batch = _LANCEDB_STORE.fused_search_batch_rerank(
+            user_ids, queries, text_vecs, image_vecs, cfg.index_topk_text, cfg.index_topk_image, cfg.rerank_topk, cfg.final_n,
+            cfg.confidence_tau, _DEVICE_CROSS_ENCODER, _METADATA_STORE)
+    else:
+        batch = fused_search(user_ids, text_vecs, image_vecs, cfg.index_topk_text, cfg.index_topk_image, cfg.final_n,
+                             cfg.confidence_tau)
+    bulk = getattr(_METADATA_STORE, "get_chunks", None)
     out: List[Tuple[List[Dict[str, Any]], bool]] = []
-    for user_id, query, (items, low) in zip(user_ids, queries, batch):
+    for user_id, query, res in zip(user_ids, queries, batch):
+        if res is None:                               # the device path could not serve this request (join failure)
+            host = retrieve(user_id, query)
+            out.append((host, _confidence_low(host)))
+            continue
+        items, low = res
+        found = bulk([it["chunk_id"] for it in items]) if (bulk and items) else None
         joined, complete = [], True
         for it in items:
-            chunk = _METADATA_STORE.get_chunk(it["chunk_id"])
+            chunk = found.get(it["chunk_id"]) if found is not None else _METADATA_STORE.get_chunk(it["chunk_id"])
             if not chunk or (it["modality"] == "text" and not chunk.text):
                 complete = False
                 break
-            joined.append({"chunk_id": chunk.id, "modality": it["modality"], "score": it["score"],
-                           "metadata": _prepare_metadata(chunk), "text": chunk.text if it["modality"] == "text" else None,
-                           "combined_score": it["combined_score"]})
+            row = {"chunk_id": chunk.id, "modality": it["modality"], "score": it["score"],
+                   "metadata": _prepare_metadata(chunk), "text": chunk.text if it["modality"] == "text" else None}
+            if "rerank_score" in it:
+                row["rerank_score"] = it["rerank_score"]
+            row["combined_score"] = it["combined_score"]
+            joined.append(row)
         if not complete:
             host = retrieve(user_id, query)
             out.append((host, _confidence_low(host)))

@@ -251,19 +251,36 @@ class _Collection:
         self._buf = self._bufs[-1]
         t0 = time.perf_counter()
         moved = 0
-        for blk in host.blocks:                             # each host block is read once per shard it lands in, in place
+        jobs = []                                           # (shard, source rows [i0, i1) of a host block, local row map)
+        for blk in host.blocks:                             # each host block is read in place, once per shard it lands in
             dst = self._res_of[blk.start:blk.start + blk.n]
-            live = dst[dst >= 0]
-            if live.size == 0:
-                continue
-            dmin, dmax = int(live.min()), int(live.max())
-            for g in range(G):
-                lo, hi = self._bounds[g], self._bounds[g + 1]
-                if dmax < lo or dmin >= hi:
-                    continue
-                local = dst if G == 1 else np.where((dst >= lo) & (dst < hi), dst - lo, -1)
-                ResidentIndex.load_rows_into(self._bufs[g], blk.emb, dst_rows=local)
+            if G == 1:
+                if (dst >= 0).any():
+                    jobs.append((0, blk.emb, dst))
+            else:
+                for g in range(G):
+                    lo, hi = self._bounds[g], self._bounds[g + 1]
+                    hit = np.nonzero((dst >= lo) & (dst < hi))[0]
+                    if hit.size == 0:
+                        continue
+                    i0, i1 = int(hit[0]), int(hit[-1]) + 1     # only the slice of the block that holds this shard's rows
+                    sub = dst[i0:i1]
+                    jobs.append((g, blk.emb[i0:i1], np.where((sub >= lo) & (sub < hi), sub - lo, -1)))
             moved += blk.n
+        if G == 1:
+            for g, src, local in jobs:
+                ResidentIndex.load_rows_into(self._bufs[g], src, dst_rows=local)
+        else:
+            # one uploader thread per device: every GPU has its own PCIe link, the C call releases the GIL
+            from concurrent.futures import ThreadPoolExecutor
+
+            def upload(g):
+                for gg, src, local in jobs:
+                    if gg == g:
+                        ResidentIndex.load_rows_into(self._bufs[g], src, dst_rows=local)
+
+            with ThreadPoolExecutor(G) as pool:
+                list(pool.map(upload, range(G)))
         dt = time.perf_counter() - t0
         self.last_load_gbs = moved * host.dim * 4 / dt / 1e9 if dt > 0 else None
         self._n_res = n
@@ -347,10 +364,15 @@ class _Collection:
             if res is None:
                 return None
             ranges = [self._ranges.get(str(u)) or [] for u in user_ids]
+            on_device = isinstance(vectors, torch.Tensor)     # e.g. straight out of a device encoder: no host hop
             if self._multi is not None:       # sharded: merged host result -> the collector device (where K5 runs)
-                s, r = self._multi.search_host(np.ascontiguousarray(vectors, dtype=np.float32), limit, ranges)
+                host_q = vectors.detach().float().cpu().numpy() if on_device else vectors
+                s, r = self._multi.search_host(np.ascontiguousarray(host_q, dtype=np.float32), limit, ranges)
                 return torch.from_numpy(s).to(self.devices[0]), torch.from_numpy(r).to(self.devices[0])
-            q = torch.from_numpy(np.ascontiguousarray(vectors, dtype=np.float32)).to(self.device)
+            if on_device:
+                q = vectors.to(device=self.device, dtype=torch.float32).contiguous()
+            else:
+                q = torch.from_numpy(np.ascontiguousarray(vectors, dtype=np.float32)).to(self.device)
             return res.search_ranges(q, limit, ranges)
 
     def row_identity(self, resident_row: int) -> int:
@@ -372,7 +394,9 @@ class _Collection:
             live = [i for i, r in enumerate(ranges) if r]
             if not live:
                 return out
-            q = np.ascontiguousarray(vectors[live], dtype=np.float32)
+            q = vectors if len(live) == len(ranges) else vectors[live]
+            if q.dtype != np.float32 or not q.flags.c_contiguous:
+                q = np.ascontiguousarray(q, dtype=np.float32)
             first = ranges[live[0]]
             if self._multi is not None:
                 # row-range shards on the GPUs of this box: one launch per device, fused exchange, mapped mailbox
@@ -387,22 +411,20 @@ class _Collection:
             else:
                 s_dev, r_dev = res.search_ranges(torch.from_numpy(q).to(self.device), limit, [ranges[i] for i in live])
                 scores, rows = s_dev.cpu().numpy(), r_dev.cpu().numpy()
-            one = np.float32(1.0)
-            host, perm = self.host, self._perm
-            valid = rows >= 0                                   # hits are a prefix of every result row
-            counts = valid.sum(axis=1)
-            hrows = perm[rows[valid]]                           # host rows of every hit of the batch, one gather
-            ids = host.values_at("chunk_id", hrows)
-            metas = host.values_at("meta", hrows)
             # Lance returns the f32 cosine distance; _format_results (:130-131) turns it into a Python float score
-            sims = (1.0 - (one - scores[valid]).astype(np.float64)).tolist()
-            pos = 0
+            one = np.float32(1.0)
+            sims = (1.0 - (one - scores).astype(np.float64)).tolist()
+            hit_rows = rows.tolist()
+            host, perm = self.host, self._perm
             for j, i in enumerate(live):
-                c = int(counts[j])
-                out[i] = [{"chunk_id": ids[p], "score": sims[p],
-                           "meta": {} if metas[p] in (None, "", "{}") else json.loads(metas[p])}
-                          for p in range(pos, pos + c)]
-                pos += c
+                rr = hit_rows[j]
+                n = len(rr) if rr[-1] >= 0 else rr.index(-1)      # hits are a prefix of the result row
+                hrows = [perm[r] for r in rr[:n]]
+                ids = host.values_at("chunk_id", hrows)
+                metas = host.values_at("meta", hrows)
+                sj = sims[j]
+                out[i] = [{"chunk_id": ids[p], "score": sj[p],
+                           "meta": {} if metas[p] in (None, "", "{}") else json.loads(metas[p])} for p in range(n)]
             return out
 
 
@@ -510,13 +532,111 @@ class B200Store:
         self._sync()
         return _fused_batch(self, list(user_ids), text_vecs, image_vecs, top_k_text, top_k_image, final_n, tau)
 
+    def fused_search_batch_rerank(self, user_ids: Sequence[str], queries: Sequence[str], text_vecs, image_vecs,
+                                  top_k_text: int, top_k_image: int, rerank_topk: int, final_n: int, tau: float,
+                                  cross_encoder, metadata_store):
+        """Rerank-ON request path kept on the device: text scan + image scan, ONE cross-encoder forward
+        pass over the (query, passage) pairs of the whole micro-batch (<= RERANK_TOPK per request, reference
+        app/ml/retrieve.py:141-148), logits left on the device, then mmr_fuse_f64 = _rerank_text's re-ordering +
+        _fuse_results + _confidence_low.  Returns per request (items, low_confidence) like fused_search_batch -- items of
+        reranked text hits also carry "rerank_score" -- or None for a request whose candidates could not be joined with
+        their text (the caller then serves it through the host path)."""
+        self._sync()
+        return _fused_batch_rerank(self, list(user_ids), list(queries), text_vecs, image_vecs, top_k_text, top_k_image,
+                                   rerank_topk, final_n, tau, cross_encoder, metadata_store)
+
+
+def _as_queries(v):
+    return v if isinstance(v, torch.Tensor) else np.asarray(v, dtype=np.float32)
+
+
+def _fused_batch_rerank(store: "B200Store", user_ids, queries, text_vecs, image_vecs, kt: int, ki: int, rerank_topk: int,
+                        final_n: int, tau: float, cross_encoder, metadata_store):
+    from .index import fuse_f64
+
+    n = len(user_ids)
+    t = store._text_table.search_device(user_ids, _as_queries(text_vecs), kt)
+    i = store._image_table.search_device(user_ids, _as_queries(image_vecs), ki)
+    if t is None and i is None:
+        return [([], True) for _ in user_ids]
+    dev = (t if t is not None else i)[0].device
+    one = torch.tensor(1.0, dtype=torch.float32, device=dev)
+
+    def py_scores(pair, k):      # _format_results: score = 1.0 - float(f32 distance); counts = hits per request
+        if pair is None:
+            return torch.zeros((n, max(k, 1)), dtype=torch.float64, device=dev), torch.zeros(n, dtype=torch.int32, device=dev), None
+        s, r = pair
+        return 1.0 - (one - s).double(), (r >= 0).sum(dim=1).to(torch.int32), r
+
+    ts, tc, tr = py_scores(t, kt)
+    is_, ic, ir = py_scores(i, ki)
+    # the cross-encoder needs the passages of the first RERANK_TOPK text hits of every request: one batched join
+    head = min(rerank_topk, ts.shape[1])
+    tr_host = tr[:, :head].cpu().numpy() if tr is not None else np.full((n, 0), -1)
+    cand_ids = [[store._text_table.chunk_id_of(int(r)) for r in row if r >= 0] for row in tr_host]
+    flat = [c for row in cand_ids for c in row]
+    bulk = getattr(metadata_store, "get_chunks", None)
+    found = bulk(flat) if (bulk and flat) else {c: metadata_store.get_chunk(c) for c in flat}
+    pairs, owner, broken = [], [], set()
+    for b, row in enumerate(cand_ids):
+        for c in row:
+            chunk = found.get(c)
+            if not chunk or not chunk.text:
+                broken.add(b)
+                break
+        if b not in broken:
+            for c in row:
+                pairs.append((queries[b], found[c].text))
+                owner.append(b)
+    rr = torch.zeros((n, ts.shape[1]), dtype=torch.float64, device=dev)
+    rc = torch.zeros(n, dtype=torch.int32, device=dev)
+    if pairs:
+        logits = cross_encoder.predict_device(pairs).to(dev).double()          # ONE forward pass for the micro-batch
+        counts = np.bincount(np.asarray(owner), minlength=n)
+        rows_idx = torch.as_tensor(owner, device=dev, dtype=torch.int64)
+        pos = torch.as_tensor(np.concatenate([np.arange(c) for c in counts]) if len(owner) else [], device=dev, dtype=torch.int64)
+        rr[rows_idx, pos] = logits
+        rc = torch.as_tensor(counts, dtype=torch.int32, device=dev)
+    out = fuse_f64(ts if t is not None else None, tc if t is not None else None, is_ if i is not None else None,
+                   ic if i is not None else None, final_n, tau, rerank=rr if t is not None else None,
+                   rerank_count=rc if t is not None else None)
+    comb, index, low = out["combined"].cpu().numpy(), out["index"].cpu().numpy(), out["low_conf"].cpu().numpy()
+    ts_h = ts.cpu().numpy() if t is not None else None
+    is_h = is_.cpu().numpy() if i is not None else None
+    tr_all = tr.cpu().numpy() if tr is not None else None
+    ir_all = ir.cpu().numpy() if ir is not None else None
+    rr_h, rc_h = rr.cpu().numpy(), rc.cpu().numpy()
+    kt_eff = ts.shape[1] if t is not None else 0
+    results = []
+    for b in range(n):
+        if b in broken:
+            results.append(None)
+            continue
+        items = []
+        for o in range(final_n):
+            ix = int(index[b, o])
+            if ix < 0:
+                break
+            if ix < kt_eff and t is not None:
+                it = {"chunk_id": store._text_table.chunk_id_of(int(tr_all[b, ix])), "modality": "text",
+                      "score": float(ts_h[b, ix])}
+                if ix < rc_h[b]:
+                    it["rerank_score"] = float(rr_h[b, ix])
+            else:
+                j = ix - kt_eff
+                it = {"chunk_id": store._image_table.chunk_id_of(int(ir_all[b, j])), "modality": "image", "score": float(is_h[b, j])}
+            it["combined_score"] = float(comb[b, o])
+            items.append(it)
+        results.append((items, bool(low[b])))
+    return results
+
 
 def _fused_batch(store: "B200Store", user_ids, text_vecs, image_vecs, kt: int, ki: int, final_n: int, tau: float):
     """scan(text) + scan(image) + K5 fusion/gate for a batch of requests, results fetched with one small D2H."""
     from .index import fuse
 
-    t = store._text_table.search_device(user_ids, np.asarray(text_vecs, dtype=np.float32), kt)
-    i = store._image_table.search_device(user_ids, np.asarray(image_vecs, dtype=np.float32), ki)
+    t = store._text_table.search_device(user_ids, _as_queries(text_vecs), kt)
+    i = store._image_table.search_device(user_ids, _as_queries(image_vecs), ki)
     if t is None and i is None:
         return [([], True) for _ in user_ids]
     out = fuse(t, i, final_n, tau)

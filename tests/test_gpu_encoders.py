@@ -158,3 +158,96 @@ def test_query_is_born_on_the_device_and_feeds_the_scan(enc_mod, bert):
     assert text_enc([]).shape == (0, 384)
     enc.close()
     ix.close()
+
+
+class _Tok:
+    """Stand-in tokenizer (the real ones need vocabulary files): words hash to ids; pairs get token types 0 / 1."""
+
+    def __init__(self, bos=101, eos=102, lo=1000, span=20000, clip=False):
+        self.bos, self.eos, self.lo, self.span, self.clip = bos, eos, lo, span, clip
+
+    def _ids(self, text):
+        import zlib
+        return [self.lo + (zlib.crc32(w.encode()) % self.span) for w in text.split()]
+
+    def __call__(self, texts, pairs=None, padding=True, truncation=True, return_tensors="np", max_length=256):
+        seqs, types = [], []
+        for n, t in enumerate(texts):
+            a = [self.bos] + self._ids(t)[: max_length - 2] + [self.eos]
+            ty = [0] * len(a)
+            if pairs is not None:
+                b = self._ids(pairs[n])[: max(0, max_length - len(a) - 1)] + [self.eos]
+                a, ty = a + b, ty + [1] * len(b)
+            seqs.append(a)
+            types.append(ty)
+        s = max(len(a) for a in seqs)
+        pad = self.eos if self.clip else 0
+        ids = np.full((len(seqs), s), pad, np.int64)
+        mask = np.zeros((len(seqs), s), np.int64)
+        tt = np.zeros((len(seqs), s), np.int64)
+        for i, (a, ty) in enumerate(zip(seqs, types)):
+            ids[i, : len(a)], mask[i, : len(a)], tt[i, : len(a)] = a, 1, ty
+        return {"input_ids": ids, "attention_mask": mask, "token_type_ids": tt}
+
+
+def test_whole_request_path_on_the_device_equals_per_request_host_path(enc_mod, bert):
+    """SURVEY 8f rank 2 + 3 end to end: B requests -> MiniLM + CLIP text tower on the device -> two scans -> ONE cross-encoder
+    pass over all (query, passage) pairs -> mmr_fuse_f64 (rerank re-ordering + z-score fusion + CONFIDENCE_TAU gate).
+    Must equal, request by request, the reference-shaped host path `retrieve()` + `_confidence_low()` driven by the same
+    models: same winners, bit-identical combined scores, same gate."""
+    from types import SimpleNamespace
+    from transformers import BertConfig, BertForSequenceClassification, CLIPTextConfig, CLIPTextModelWithProjection
+    from tests import util
+    mmr = importlib.import_module(PKG)
+    retrieve = importlib.import_module(PKG + ".retrieve")
+    cache = importlib.import_module(PKG + ".cache")
+    settings_mod = importlib.import_module(PKG + ".settings")
+    torch.manual_seed(7)
+    clip = _round_linear_weights(_spread(CLIPTextModelWithProjection(CLIPTextConfig(num_hidden_layers=4)), 2.0))
+    cross = _round_linear_weights(_spread(BertForSequenceClassification(BertConfig(
+        vocab_size=30522, hidden_size=384, num_hidden_layers=6, num_attention_heads=12, intermediate_size=1536, num_labels=1))))
+    text_enc = enc_mod.TextQueryEncoder(_Tok(), enc_mod.DeviceEncoder.from_hf_bert(bert))
+    image_enc = enc_mod.ImageQueryEncoder(_Tok(bos=49406, eos=49407, span=40000, clip=True), enc_mod.DeviceEncoder.from_hf_clip(clip))
+    tok = _Tok()
+    cross_enc = enc_mod.DeviceCrossEncoder(lambda a, b, **kw: tok(a, pairs=b, max_length=kw.get("max_length", 512)),
+                                           enc_mod.DeviceEncoder.from_hf_bert(cross))
+    n_t, n_i = 6000, 2500
+    users = ["u0", "u1", "u2"]
+    store = mmr.B200Store()
+    store.load_arrow("text_collection", mmr.make_arrow_table([f"t{i}" for i in range(n_t)], [users[i % 3] for i in range(n_t)],
+                                                             ["d"] * n_t, ["text"] * n_t, util.unit_rows(n_t, 384, 71), ["{}"] * n_t))
+    store.load_arrow("image_collection", mmr.make_arrow_table([f"i{i}" for i in range(n_i)], [users[i % 3] for i in range(n_i)],
+                                                              ["d"] * n_i, ["image"] * n_i, util.unit_rows(n_i, 512, 72), ["{}"] * n_i))
+    chunks = {f"t{i}": SimpleNamespace(id=f"t{i}", document_id="d", modality="text", text=f"passage number {i} about topic {i % 17}",
+                                       meta={}, page_no=i, start_ts=None, end_ts=None, file_path=None) for i in range(n_t)}
+    chunks.update({f"i{i}": SimpleNamespace(id=f"i{i}", document_id="d", modality="image", text=None, meta={}, page_no=None,
+                                            start_ts=None, end_ts=None, file_path=f"/f/{i}.jpg") for i in range(n_i)})
+    meta = SimpleNamespace(get_chunk=chunks.get, get_chunks=lambda ids: {c: chunks[c] for c in ids if c in chunks})
+    cache.clear_all_caches()
+    retrieve.configure(store=store, metadata=meta, device_text_encoder=text_enc, device_image_encoder=image_enc,
+                       device_cross_encoder=cross_enc, retrieval_settings=settings_mod.RetrievalSettings(use_rerank=True))
+    queries = [f"question {j} about topic {j % 5} and retrieval" for j in range(7)]
+    who = [users[j % 3] for j in range(7)]
+    got = retrieve.retrieve_batch_device(who, queries)
+    for j in range(7):
+        cache.clear_all_caches()
+        host = retrieve.retrieve(who[j], queries[j])
+        items, low = got[j]
+        assert [it["chunk_id"] for it in items] == [h["chunk_id"] for h in host], j
+        assert [it["combined_score"] for it in items] == [h["combined_score"] for h in host], j
+        assert [it.get("rerank_score") for it in items] == [h.get("rerank_score") for h in host], j
+        assert low is retrieve._confidence_low(host)
+        assert len(items) == 4 and all("metadata" in it for it in items)
+    # rerank off: same comparison through mmr_fuse
+    retrieve.configure(retrieval_settings=settings_mod.RetrievalSettings(use_rerank=False))
+    cache.clear_all_caches()
+    got = retrieve.retrieve_batch_device(who, queries)
+    for j in range(7):
+        cache.clear_all_caches()
+        host = retrieve.retrieve(who[j], queries[j])
+        assert [it["chunk_id"] for it in got[j][0]] == [h["chunk_id"] for h in host]
+        assert [it["combined_score"] for it in got[j][0]] == [h["combined_score"] for h in host]
+    cache.clear_all_caches()
+    retrieve.configure(retrieval_settings=settings_mod.RetrievalSettings())
+    retrieve._DEVICE_TEXT_ENCODER = retrieve._DEVICE_IMAGE_ENCODER = retrieve._DEVICE_CROSS_ENCODER = None
+    retrieve._CROSS_ENCODER = None
