@@ -51,7 +51,8 @@ struct Options {
   int umma_pair = 1;      // MMR_UMMA_PAIR=0  single CTAs instead of CTA pairs
   int umma_noprobe = 0;   // MMR_UMMA_NOPROBE=1
   int force_family = 0;   // MMR_FORCE_FAMILY 1 = K1, 2 = K2 regardless of batch size
-  int umma_lockstep = 1;      // MMR_UMMA_LOCKSTEP=0  CTA pairs of one row slot run unsynchronised (measurement)
+  int umma_lockstep = 0;      // MMR_UMMA_LOCKSTEP=1  CTA pairs of one row slot keep within a window of tiles (measured SLOWER:
+                              //                      profiles/r02_k2_summary.md; kept as a measurement switch)
   int inline_query = 1;   // MMR_INLINE_QUERY=0  host-buffer calls always stage the query with an H2D copy (measurement)
   int mailbox = 0;        // MMR_MAILBOX=1       host-buffer calls spin on a flag the kernel writes into the mapped mailbox instead
                           //                     of synchronising the stream (measured no faster: profiles/r02_fixed_cost.json)

@@ -143,6 +143,17 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
     for (int c = 0; c < ENC_NT / 32; ++c) {
       uint32_t v[32];
       tmem_ld_x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c * 32), v);
+      float res[32];
+      if constexpr (EPI == EPI_BIAS_RES_F32) {
+        // all residual loads are issued before the first store: `out` may alias `residual` (in-place residual stream), and
+        // a load-store-load chain through possibly aliasing pointers serialises on global-memory latency
+        // (36 us per GEMM in the first profile, profiles/r02_encoder_summary.md)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int t = t0 + c * 32 + j;
+          res[j] = t < p.M ? __ldcg(p.residual + size_t(t) * p.N + f) : 0.f;
+        }
+      }
       tmem_wait_ld();
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -153,7 +164,7 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
           if constexpr (EPI == EPI_BIAS_F32) {
             p.out_f32[o] = y;
           } else if constexpr (EPI == EPI_BIAS_RES_F32) {
-            p.out_f32[o] = y + p.residual[o];
+            p.out_f32[o] = y + res[j];
           } else if constexpr (EPI == EPI_GELU_BF16) {
             p.out_bf16[o] = __float2bfloat16_rn(gelu_erf(y));
           } else {
@@ -243,74 +254,121 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
 }
 
 // ---------------------------------------------------------------------------------------------- attention
-// grid = (heads, B); one CTA = one head of one sequence; K (padded rows) and V of the head in shared memory (fp32);
-// warp w handles query rows w, w + NW, ...: scores over keys (lane = key), softmax with warp reductions, P in shared
-// memory, context with lane = output dim.  mask[b, j] == 0 hides key j (padding); causal hides j > i (CLIP).
+// grid = (heads, B); one CTA = one head of one sequence; K (rows padded by 4 floats) and V of the head in shared memory
+// (fp32).  A warp handles ATT_RQ query rows at a time: scores with lane = key (the K row is read once, as float4, for all
+// ATT_RQ rows; the query rows are broadcast reads from shared memory; independent accumulators, no shuffles in the inner
+// loop), softmax with warp reductions, P in shared memory, context with lane = output dim.
+// mask[b, j] == 0 hides key j (padding); causal hides j > i (CLIP).
+constexpr int ATT_NW = 8;   // warps per CTA
+constexpr int ATT_RQ = 4;   // query rows per warp per pass
+
 template <int DH>
-__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ mask,
-                                                        __nv_bfloat16* __restrict__ ctx, int S, int H, int causal) {
+inline size_t attention_smem_bytes(int S) {
+  return (size_t(S) * (DH + 4) + size_t(S) * DH + size_t(ATT_NW) * ATT_RQ * DH + size_t(ATT_NW) * ATT_RQ * S) * 4;
+}
+
+template <int DH>
+__global__ void __launch_bounds__(ATT_NW * 32) attention_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ mask,
+                                                               __nv_bfloat16* __restrict__ ctx, int S, int H, int causal) {
   extern __shared__ __align__(16) float att_smem[];
   pdl_chain_prologue();
-  constexpr int NW = 8;
-  constexpr int KP = DH + 1;              // padded K row: lanes read different rows at the same column
+  constexpr int KP = DH + 4;              // padded K row: float4 reads of different rows by a quarter warp hit distinct banks
   constexpr int DPL = DH / 32;            // output dims per lane
   const int h = blockIdx.x, b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* Ks = att_smem;                   // [S][KP]
-  float* Vs = Ks + size_t(S) * KP;        // [S][DH]
-  float* Ps = Vs + size_t(S) * DH;        // [NW][S]
+  float* Ks = att_smem;                                   // [S][KP]
+  float* Vs = Ks + size_t(S) * KP;                        // [S][DH]
+  float* Qs = Vs + size_t(S) * DH + size_t(warp) * ATT_RQ * DH;                          // this warp's [RQ][DH]
+  float* Ps = Vs + size_t(S) * DH + size_t(ATT_NW) * ATT_RQ * DH + size_t(warp) * ATT_RQ * S;   // this warp's [RQ][S]
   const size_t row0 = size_t(b) * S;
   const int ld = 3 * H;
-  for (int i = threadIdx.x; i < S * DH; i += blockDim.x) {
-    const int j = i / DH, d = i % DH;
-    const float* src = qkv + (row0 + j) * ld + h * DH + d;
-    Ks[j * KP + d] = src[H];
-    Vs[j * DH + d] = src[2 * H];
+  for (int i = threadIdx.x; i < S * (DH / 4); i += blockDim.x) {
+    const int j = i / (DH / 4), d4 = i % (DH / 4);
+    const float* src = qkv + (row0 + j) * ld + h * DH + d4 * 4;
+    *reinterpret_cast<float4*>(Ks + j * KP + d4 * 4) = *reinterpret_cast<const float4*>(src + H);
+    *reinterpret_cast<float4*>(Vs + j * DH + d4 * 4) = *reinterpret_cast<const float4*>(src + 2 * H);
   }
   __syncthreads();
   const float scale = rsqrtf(float(DH));
-  float* P = Ps + size_t(warp) * S;
-  for (int i = warp; i < S; i += NW) {
-    float q[DPL];
+  for (int i0 = warp * ATT_RQ; i0 < S; i0 += ATT_NW * ATT_RQ) {
+    // stage the (scaled) query rows of this pass
+    for (int e = lane; e < ATT_RQ * DH; e += 32) {
+      const int r = e / DH, d = e % DH;
+      Qs[e] = (i0 + r < S) ? qkv[(row0 + i0 + r) * ld + h * DH + d] * scale : 0.f;
+    }
+    __syncwarp();
+    const int jend = causal ? min(S, i0 + ATT_RQ) : S;
+    float mx[ATT_RQ];
 #pragma unroll
-    for (int u = 0; u < DPL; ++u) q[u] = qkv[(row0 + i) * ld + h * DH + u * 32 + lane] * scale;
-    const int jend = causal ? i + 1 : S;
-    float mx = -INFINITY;
+    for (int r = 0; r < ATT_RQ; ++r) mx[r] = -INFINITY;
     for (int j0 = 0; j0 < jend; j0 += 32) {
       const int j = j0 + lane;
-      float s = 0.f;
       const float* kr = Ks + size_t(min(j, S - 1)) * KP;
+      float sc[ATT_RQ];
 #pragma unroll
-      for (int u = 0; u < DPL; ++u)
+      for (int r = 0; r < ATT_RQ; ++r) sc[r] = 0.f;
 #pragma unroll
-        for (int d = 0; d < 32; ++d) s = fmaf(__shfl_sync(0xffffffffu, q[u], d), kr[u * 32 + d], s);
-      const bool ok = j < jend && (mask == nullptr || mask[row0 + j] != 0);
-      s = ok ? s : -INFINITY;
-      if (j < S) P[j] = s;
-      mx = fmaxf(mx, s);
+      for (int d4 = 0; d4 < DH / 4; ++d4) {
+        const float4 k4 = *reinterpret_cast<const float4*>(kr + d4 * 4);
+#pragma unroll
+        for (int r = 0; r < ATT_RQ; ++r) {
+          const float4 q4 = *reinterpret_cast<const float4*>(Qs + r * DH + d4 * 4);   // broadcast
+          sc[r] = fmaf(q4.x, k4.x, fmaf(q4.y, k4.y, fmaf(q4.z, k4.z, fmaf(q4.w, k4.w, sc[r]))));
+        }
+      }
+      const bool key_ok = j < S && (mask == nullptr || mask[row0 + min(j, S - 1)] != 0);
+#pragma unroll
+      for (int r = 0; r < ATT_RQ; ++r) {
+        const bool ok = key_ok && j < jend && (!causal || j <= i0 + r);
+        const float v = ok ? sc[r] : -INFINITY;
+        if (j < S) Ps[r * S + j] = v;
+        mx[r] = fmaxf(mx[r], v);
+      }
     }
+    float sum[ATT_RQ];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    for (int r = 0; r < ATT_RQ; ++r) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], o));
+      sum[r] = 0.f;
+    }
     __syncwarp();
-    float sum = 0.f;
     for (int j = lane; j < jend; j += 32) {
-      const float e = (mx == -INFINITY) ? 0.f : __expf(P[j] - mx);
-      P[j] = e;
-      sum += e;
+#pragma unroll
+      for (int r = 0; r < ATT_RQ; ++r) {
+        const float e = (mx[r] == -INFINITY) ? 0.f : __expf(Ps[r * S + j] - mx[r]);
+        Ps[r * S + j] = e;
+        sum[r] += e;
+      }
     }
-    sum = warp_allreduce_sum(sum);
+#pragma unroll
+    for (int r = 0; r < ATT_RQ; ++r) sum[r] = warp_allreduce_sum(sum[r]);
     __syncwarp();
-    float acc[DPL];
+    float acc[ATT_RQ][DPL];
 #pragma unroll
-    for (int u = 0; u < DPL; ++u) acc[u] = 0.f;
+    for (int r = 0; r < ATT_RQ; ++r)
+#pragma unroll
+      for (int u = 0; u < DPL; ++u) acc[r][u] = 0.f;
     for (int j = 0; j < jend; ++j) {
-      const float pj = P[j];
+      float vv[DPL];
 #pragma unroll
-      for (int u = 0; u < DPL; ++u) acc[u] = fmaf(pj, Vs[j * DH + u * 32 + lane], acc[u]);
+      for (int u = 0; u < DPL; ++u) vv[u] = Vs[j * DH + u * 32 + lane];
+#pragma unroll
+      for (int r = 0; r < ATT_RQ; ++r) {
+        const float pj = Ps[r * S + j];   // broadcast
+#pragma unroll
+        for (int u = 0; u < DPL; ++u) acc[r][u] = fmaf(pj, vv[u], acc[r][u]);
+      }
     }
-    const float inv = sum > 0.f ? 1.f / sum : 0.f;
 #pragma unroll
-    for (int u = 0; u < DPL; ++u) ctx[(row0 + i) * H + h * DH + u * 32 + lane] = __float2bfloat16_rn(acc[u] * inv);
+    for (int r = 0; r < ATT_RQ; ++r) {
+      if (i0 + r < S) {
+        const float inv = sum[r] > 0.f ? 1.f / sum[r] : 0.f;
+#pragma unroll
+        for (int u = 0; u < DPL; ++u)
+          ctx[(row0 + i0 + r) * H + h * DH + u * 32 + lane] = __float2bfloat16_rn(acc[r][u] * inv);
+      }
+    }
     __syncwarp();
   }
 }
@@ -380,12 +438,19 @@ __global__ void clip_head_kernel(const float* __restrict__ x, const int32_t* __r
   const float rstd = rsqrtf(block_sum(d * d, red) / float(H) + eps);
   head_smem[c] = d * rstd * ln_g[c] + ln_b[c];
   __syncthreads();
-  float e = 0.f;
-  if (c < P) {
-    const float* w = proj + size_t(c) * H;
-    for (int i = 0; i < H; ++i) e = fmaf(w[i], head_smem[i], e);
+  // projection: warp w computes outputs w, w + nwarps, ... with coalesced reads of the weight rows
+  float* proj_out = head_smem + H;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int o = warp; o < P; o += nwarps) {
+    const float* w = proj + size_t(o) * H;
+    float a = 0.f;
+    for (int i = lane; i < H; i += 32) a = fmaf(w[i], head_smem[i], a);
+    a = warp_allreduce_sum(a);
+    if (lane == 0) proj_out[o] = a;
   }
-  const float nrm = sqrtf(block_sum(c < P ? e * e : 0.f, red));
+  __syncthreads();
+  const float e = c < P ? proj_out[c] : 0.f;
+  const float nrm = sqrtf(block_sum(e * e, red));
   if (c < P) out[size_t(b) * P + c] = nrm > 0.f ? e / nrm : e;
 }
 
@@ -399,10 +464,17 @@ __global__ void cross_head_kernel(const float* __restrict__ x, int S, int H, con
   const int b = blockIdx.x, c = threadIdx.x;
   head_smem[c] = x[(size_t(b) * S) * H + c];
   __syncthreads();
-  const float* w = pool_w + size_t(c) * H;
-  float e = pool_b[c];
-  for (int i = 0; i < H; ++i) e = fmaf(w[i], head_smem[i], e);
-  const float logit = block_sum(tanhf(e) * cls_w[c], red);
+  float* pooled = head_smem + H;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int o = warp; o < H; o += nwarps) {     // coalesced reads of the pooler's weight rows
+    const float* w = pool_w + size_t(o) * H;
+    float a = 0.f;
+    for (int i = lane; i < H; i += 32) a = fmaf(w[i], head_smem[i], a);
+    a = warp_allreduce_sum(a);
+    if (lane == 0) pooled[o] = tanhf(a + pool_b[o]);
+  }
+  __syncthreads();
+  const float logit = block_sum(pooled[c] * cls_w[c], red);
   if (c == 0) out[b] = logit + cls_b[0];
 }
 

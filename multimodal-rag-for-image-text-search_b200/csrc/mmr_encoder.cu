@@ -260,12 +260,12 @@ static int forward_t(mmr_encoder* e, int B, int S, float* out_dev, cudaStream_t 
   int dev = 0;
   cudaGetDevice(&dev);
   if (!att_attr[dev & 63]) {
-    CUDA_TRY(cudaFuncSetAttribute(attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     att_attr[dev & 63] = true;
   }
-  const size_t att_smem = (size_t(S) * (DH + 1) + size_t(S) * DH + size_t(8) * S) * 4;
-  if (att_smem > 200 * 1024) return fail(MMR_ERR_UNSUPPORTED, "sequence length %d does not fit the attention kernel", S);
+  const size_t att_smem = DH == 32 ? attention_smem_bytes<32>(S) : attention_smem_bytes<64>(S);
+  if (att_smem > 220 * 1024) return fail(MMR_ERR_UNSUPPORTED, "sequence length %d does not fit the attention kernel", S);
 
   // embeddings
   if (clip)
@@ -286,10 +286,10 @@ static int forward_t(mmr_encoder* e, int B, int S, float* out_dev, cudaStream_t 
     rc = launch_gemm<EPI_BIAS_F32>(L.m_qkv, e->m_x16, M, 3 * H, H, L.qkv_b, nullptr, e->qkv, nullptr, st);
     if (rc != MMR_OK) return rc;
     if (DH == 32)
-      CUDA_TRY(launch_pdl(attention_kernel<32>, dim3(c.heads, B), dim3(256), att_smem, st, e->qkv, e->d_mask, e->ctx16, S, H,
+      CUDA_TRY(launch_pdl(attention_kernel<32>, dim3(c.heads, B), dim3(ATT_NW * 32), att_smem, st, e->qkv, e->d_mask, e->ctx16, S, H,
                           clip ? 1 : 0));
     else
-      CUDA_TRY(launch_pdl(attention_kernel<64>, dim3(c.heads, B), dim3(256), att_smem, st, e->qkv, e->d_mask, e->ctx16, S, H,
+      CUDA_TRY(launch_pdl(attention_kernel<64>, dim3(c.heads, B), dim3(ATT_NW * 32), att_smem, st, e->qkv, e->d_mask, e->ctx16, S, H,
                           clip ? 1 : 0));
     mmr_g_launches++;
     if (clip) {
@@ -321,10 +321,10 @@ static int forward_t(mmr_encoder* e, int B, int S, float* out_dev, cudaStream_t 
   if (c.kind == MMR_ENC_MINILM)
     CUDA_TRY(launch_pdl(mean_pool_norm_kernel, dim3(B), dim3(H), 0, st, e->x, e->d_mask, S, H, out_dev));
   else if (clip)
-    CUDA_TRY(launch_pdl(clip_head_kernel, dim3(B), dim3(H), size_t(H) * 4, st, e->x, e->d_ids, S, H, c.eos_token_id,
+    CUDA_TRY(launch_pdl(clip_head_kernel, dim3(B), dim3(H), size_t(H + c.proj_dim) * 4, st, e->x, e->d_ids, S, H, c.eos_token_id,
                         e->final_ln_w, e->final_ln_b, c.ln_eps, e->proj_w, c.proj_dim, out_dev));
   else
-    CUDA_TRY(launch_pdl(cross_head_kernel, dim3(B), dim3(H), size_t(H) * 4, st, e->x, S, H, e->pool_w, e->pool_b, e->cls_w,
+    CUDA_TRY(launch_pdl(cross_head_kernel, dim3(B), dim3(H), size_t(2 * H) * 4, st, e->x, S, H, e->pool_w, e->pool_b, e->cls_w,
                         e->cls_b, out_dev));
   mmr_g_launches++;
   return MMR_OK;
