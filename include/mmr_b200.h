@@ -48,7 +48,11 @@ enum mmr_dtype {
 
 enum mmr_query_precision {
   MMR_QP_AUTO = 0, /* batches of >= 3 queries on one row range run on the tensor cores with 16-bit queries */
-  MMR_QP_F32 = 1   /* every query is scored in fp32 (K1 family): a request's result is independent of its batch */
+  MMR_QP_F32 = 1,  /* every query is scored in fp32 (K1 family): a request's result is independent of its batch */
+  MMR_QP_RESCORE = 2 /* batches of >= 3 on one row range: the tensor cores nominate 32 / 64 candidates per query, which are
+                      * re-scored with the fp32 query in K1's arithmetic; the top-k is proven equal to K1's (else that
+                      * query is rerun on K1), so results are bit-identical to single-query searches.  The call
+                      * synchronises the stream once. */
 };
 
 #define MMR_MAX_K 64 /* INDEX_TOPK_TEXT defaults to 50, INDEX_TOPK_IMG to 12 (reference config.py:46-47) */
@@ -275,6 +279,8 @@ int64_t mmr_launch_count(void);
 int mmr_device_sm_count(int device, int* out_sms);
 /* Which kernel family the last mmr_search on this thread used: 1 = K1 stream, 2 = K2 umma, 3 = varlen. */
 int mmr_last_kernel(void);
+/* Queries the rescoring mode could not prove exact and reran on K1, since load. */
+int64_t mmr_rescore_reruns(void);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,7 @@ MMR_OK = 0
 MMR_BF16, MMR_F32, MMR_F16 = 0, 1, 2
 MMR_MAX_K = 64
 ABI_VERSION = 2
-MMR_QP_AUTO, MMR_QP_F32 = 0, 1
+MMR_QP_AUTO, MMR_QP_F32, MMR_QP_RESCORE = 0, 1, 2
 
 # every symbol include/mmr_b200.h declares: (name, restype, argtypes)
 _i32, _i64, _sz, _p, _f64 = C.c_int32, C.c_int64, C.c_size_t, C.c_void_p, C.c_double
@@ -54,6 +54,7 @@ SYMBOLS = [
     ("mmr_launch_count", _i64, []),
     ("mmr_device_sm_count", C.c_int, [C.c_int, C.POINTER(C.c_int)]),
     ("mmr_last_kernel", C.c_int, []),
+    ("mmr_rescore_reruns", _i64, []),
 ]
 
 

@@ -32,6 +32,7 @@ using namespace mmr;
 thread_local std::string mmr_g_err;
 std::atomic<int64_t> mmr_g_launches{0};
 static thread_local int g_last_kernel = 0;
+static std::atomic<int64_t> g_rescore_reruns{0};
 #define g_err mmr_g_err
 #define g_launches mmr_g_launches
 #define fail mmr_fail
@@ -57,6 +58,8 @@ struct mmr_index {
   std::vector<int64_t> seg;  // [n_segments + 1]
   int sm_count = 0;
   int query_precision = MMR_QP_AUTO;
+  mutable uint8_t* h_flags = nullptr;   // pinned: per-query "proven exact" flags of the rescoring mode
+  mutable int flags_cap = 0;
   // Host-buffer calls (mmr_search_host & co): one staging set per index, serialised by host_mu.
   //   h_q / d_q      pinned + device copy of the queries (only when they do not ride in the kernel parameters)
   //   h_box / d_box  MAPPED pinned mailbox: [flag u32 | pad to 64][scores f32 B*k | pad][rows i64 B*k]; the kernels write
@@ -141,6 +144,7 @@ extern "C" int mmr_abi_version(void) { return MMR_ABI_VERSION; }
 extern "C" const char* mmr_last_error(void) { return g_err.c_str(); }
 extern "C" int64_t mmr_launch_count(void) { return g_launches.load(); }
 extern "C" int mmr_last_kernel(void) { return g_last_kernel; }
+extern "C" int64_t mmr_rescore_reruns(void) { return g_rescore_reruns.load(); }
 
 extern "C" int mmr_device_sm_count(int device, int* out_sms) {
   if (!out_sms) return fail(MMR_ERR_INVALID, "out_sms is NULL");
@@ -197,6 +201,9 @@ extern "C" int mmr_index_update(mmr_index* ix, int64_t n_rows, const void* rows_
 }
 
 static void free_staging(mmr_index* ix) {
+  if (ix->h_flags) cudaFreeHost(ix->h_flags);
+  ix->h_flags = nullptr;
+  ix->flags_cap = 0;
   if (ix->h_q) cudaFreeHost(ix->h_q);
   if (ix->h_box) cudaFreeHost(ix->h_box);
   if (ix->d_q) cudaFree(ix->d_q);
@@ -217,7 +224,8 @@ extern "C" int mmr_index_destroy(mmr_index* ix) {
 
 extern "C" int mmr_index_set_query_precision(mmr_index* ix, int mode) {
   if (!ix) return fail(MMR_ERR_INVALID, "index is NULL");
-  if (mode != MMR_QP_AUTO && mode != MMR_QP_F32) return fail(MMR_ERR_INVALID, "unknown query precision %d", mode);
+  if (mode != MMR_QP_AUTO && mode != MMR_QP_F32 && mode != MMR_QP_RESCORE)
+    return fail(MMR_ERR_INVALID, "unknown query precision %d", mode);
   ix->query_precision = mode;
   return MMR_OK;
 }
@@ -431,6 +439,21 @@ static int64_t varlen_item_cap(const mmr_index* ix, int64_t n_ranges) {
   return int64_t(ix->sm_count) * K1_NW * VARLEN_ITEMS_PER_WARP + n_ranges + 64;
 }
 
+// The tensor-core slice at the END of the workspace: K2's own buffers sized for the largest k (the rescoring mode runs K2
+// with more candidates than the caller's k), then the rescoring buffers: candidate scores / rows [B, 64], ||q - q16|| [B],
+// exact flags [B].
+static size_t rescore_extra_bytes(int B) {
+  return align_up(size_t(B) * MMR_MAX_K * 4, 256) + align_up(size_t(B) * MMR_MAX_K * 8, 256) + align_up(size_t(B) * 4, 256) +
+         align_up(size_t(B), 256);
+}
+static size_t k2_slice_bytes(const mmr_index* ix, int B) {
+#ifdef MMR_WITH_UMMA
+  return umma_workspace_bytes(ix->sm_count, ix->dim, B, MMR_MAX_K) + rescore_extra_bytes(B);
+#else
+  return 0;
+#endif
+}
+
 static size_t workspace_bytes_for(const mmr_index* ix, int32_t B, int32_t k, int64_t n_ranges) {
   if (!ix || B <= 0 || k <= 0) return 0;
   const size_t kk = size_t(std::min<int32_t>(k, MMR_MAX_K));
@@ -439,9 +462,7 @@ static size_t workspace_bytes_for(const mmr_index* ix, int32_t B, int32_t k, int
   const size_t varlen = align_up(items * K1_ITEM_NQ * kk * 8, 256) + align_up(items * sizeof(ScanItem), 256) +
                         align_up(size_t(B) * sizeof(QuerySlot), 256);
   size_t total = WS_CTRL + align_up(std::max(uniform, varlen), 256);
-#ifdef MMR_WITH_UMMA
-  total += umma_workspace_bytes(ix->sm_count, ix->dim, B, int(kk));
-#endif
+  total += k2_slice_bytes(ix, B);
   return total;
 }
 
@@ -589,10 +610,7 @@ static int search_varlen_stream(const mmr_index* ix, const float* q, const std::
   const size_t part_bytes = align_up(size_t(std::max(n_items, 1)) * K1_ITEM_NQ * k * 8, 256);
   const size_t item_bytes = align_up(size_t(std::max(n_items, 1)) * sizeof(ScanItem), 256);
   const size_t slot_bytes = align_up(size_t(B) * sizeof(QuerySlot), 256);
-  size_t k2_bytes = 0;
-#ifdef MMR_WITH_UMMA
-  k2_bytes = umma_workspace_bytes(ix->sm_count, ix->dim, B, k);
-#endif
+  const size_t k2_bytes = k2_slice_bytes(ix, B);
   if (WS_CTRL + part_bytes + item_bytes + slot_bytes + k2_bytes > ws_bytes)
     return fail(MMR_ERR_WORKSPACE,
                 "workspace too small for %d work items over %lld row ranges: size it with "
@@ -630,16 +648,73 @@ static int search_varlen_stream(const mmr_index* ix, const float* q, const std::
   return MMR_OK;
 }
 
+#ifdef MMR_WITH_UMMA
+template <typename E, int D>
+static void launch_rescore_ed(const mmr_index* ix, const float* q, const float* cs, const int64_t* cr, const float* qerr, int B,
+                              int kc, int k, float* out_s, int64_t* out_r, uint8_t* flags, cudaStream_t st) {
+  if (k <= 32)
+    rescore_kernel<E, D, 1><<<B, 256, 0, st>>>(ix->rows, q, cs, cr, qerr, kc, k, ix->row_base, out_s, out_r, flags);
+  else
+    rescore_kernel<E, D, 2><<<B, 256, 0, st>>>(ix->rows, q, cs, cr, qerr, kc, k, ix->row_base, out_s, out_r, flags);
+}
+
+// MMR_QP_RESCORE: the tensor cores nominate kc candidates per query, rescore_kernel re-scores them with the fp32 query in
+// K1's arithmetic and proves the top-k exact; unproven queries (rare) are rerun on K1.  The result is bit-identical to
+// searching every query alone -- at the price of one stream synchronisation inside the call (the flags are read on the host).
+static int search_rescored(const mmr_index* ix, const float* q, int B, int k, uint32_t r0, uint32_t r1, float* out_s,
+                           int64_t* out_r, uint8_t* ws, size_t ws_total, cudaStream_t st) {
+  const int kc = k <= 16 ? 32 : MMR_MAX_K;
+  uint8_t* slice = ws + ws_total - k2_slice_bytes(ix, B);
+  uint8_t* extra = slice + umma_workspace_bytes(ix->sm_count, ix->dim, B, MMR_MAX_K);
+  float* cand_s = reinterpret_cast<float*>(extra);
+  int64_t* cand_r = reinterpret_cast<int64_t*>(extra + align_up(size_t(B) * MMR_MAX_K * 4, 256));
+  float* qerr = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(cand_r) + align_up(size_t(B) * MMR_MAX_K * 8, 256));
+  uint8_t* flags = reinterpret_cast<uint8_t*>(qerr) + align_up(size_t(B) * 4, 256);
+  int rc = umma_search(ix->umma, ix->umma2, ix->rows, ix->n_rows, ix->dim, ix->dtype, ix->sm_count, q, B, kc, r0, r1,
+                       ix->row_base, cand_s, cand_r, slice, st, g_err, nullptr, 0, qerr);
+  if (rc != MMR_OK) return rc;
+  g_launches += umma_launches_per_search();
+  if (ix->dtype == MMR_BF16 && ix->dim == 512) launch_rescore_ed<__nv_bfloat16, 512>(ix, q, cand_s, cand_r, qerr, B, kc, k, out_s, out_r, flags, st);
+  else if (ix->dtype == MMR_BF16) launch_rescore_ed<__nv_bfloat16, 384>(ix, q, cand_s, cand_r, qerr, B, kc, k, out_s, out_r, flags, st);
+  else if (ix->dim == 512) launch_rescore_ed<__half, 512>(ix, q, cand_s, cand_r, qerr, B, kc, k, out_s, out_r, flags, st);
+  else launch_rescore_ed<__half, 384>(ix, q, cand_s, cand_r, qerr, B, kc, k, out_s, out_r, flags, st);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  if (ix->flags_cap < B) {
+    if (ix->h_flags) cudaFreeHost(ix->h_flags);
+    ix->h_flags = nullptr;
+    CUDA_TRY(cudaMallocHost(&ix->h_flags, size_t(std::max(B, 1024))));
+    ix->flags_cap = std::max(B, 1024);
+  }
+  CUDA_TRY(cudaMemcpyAsync(ix->h_flags, flags, size_t(B), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  g_last_kernel = 2;
+  int reruns = 0;
+  for (int b = 0; b < B; ++b) {
+    if (ix->h_flags[b]) continue;
+    QuerySrc one;
+    one.dev = q + size_t(b) * ix->dim;
+    rc = search_uniform_stream(ix, one, 1, k, r0, r1, out_s + size_t(b) * k, out_r + size_t(b) * k, ws, st);
+    if (rc != MMR_OK) return rc;
+    ++reruns;
+  }
+  g_last_kernel = 2;
+  g_rescore_reruns += reruns;
+  return MMR_OK;
+}
+#endif
+
 // One shared row range for the whole batch: K2 when allowed and preferred, else K1 passes.
 static int search_uniform(const mmr_index* ix, QuerySrc q, int B, int k, uint32_t r0, uint32_t r1, float* out_s,
                           int64_t* out_r, uint8_t* ws, size_t ws_total, cudaStream_t st, const ExchangeInfo* xi = nullptr,
                           Completion* done = nullptr) {
 #ifdef MMR_WITH_UMMA
-  if (q.dev != nullptr && ix->query_precision == MMR_QP_AUTO &&
+  if (q.dev != nullptr && ix->query_precision != MMR_QP_F32 &&
       umma_preferred(ix->dtype, ix->dim, B, k, int64_t(r1) - r0)) {
+    if (ix->query_precision == MMR_QP_RESCORE)
+      return search_rescored(ix, q.dev, B, k, r0, r1, out_s, out_r, ws, ws_total, st);
     int rc = umma_search(ix->umma, ix->umma2, ix->rows, ix->n_rows, ix->dim, ix->dtype, ix->sm_count, q.dev, B, k, r0, r1,
-                         ix->row_base, out_s, out_r, ws + ws_total - umma_workspace_bytes(ix->sm_count, ix->dim, B, k), st,
-                         g_err);
+                         ix->row_base, out_s, out_r, ws + ws_total - k2_slice_bytes(ix, B), st, g_err);
     if (rc == MMR_OK) {
       g_launches += umma_launches_per_search();
       g_last_kernel = 2;
@@ -653,7 +728,7 @@ static int search_uniform(const mmr_index* ix, QuerySrc q, int B, int k, uint32_
 // true when a uniform batch of B queries would run on the tensor-core family
 static bool uniform_takes_k2(const mmr_index* ix, int B, int k, int64_t nrows) {
 #ifdef MMR_WITH_UMMA
-  return ix->query_precision == MMR_QP_AUTO && umma_preferred(ix->dtype, ix->dim, B, k, nrows);
+  return ix->query_precision != MMR_QP_F32 && umma_preferred(ix->dtype, ix->dim, B, k, nrows);
 #else
   return false;
 #endif
@@ -1296,7 +1371,7 @@ extern "C" int mmr_debug_umma_scores(const mmr_index* ix, const float* queries_d
   if (ix->dtype != MMR_BF16 && ix->dtype != MMR_F16) return fail(MMR_ERR_UNSUPPORTED, "K2 needs bf16 or fp16 rows");
   if (B <= 0 || row_begin < 0 || row_end > ix->n_rows || row_end <= row_begin || out_ld < row_end - row_begin)
     return fail(MMR_ERR_INVALID, "bad range");
-  if (workspace_bytes < umma_workspace_bytes(ix->sm_count, ix->dim, B, 10)) return fail(MMR_ERR_WORKSPACE, "workspace too small");
+  if (workspace_bytes < umma_workspace_bytes(ix->sm_count, ix->dim, B, MMR_MAX_K)) return fail(MMR_ERR_WORKSPACE, "workspace too small");
   int rc = umma_search(ix->umma, ix->umma2, ix->rows, ix->n_rows, ix->dim, ix->dtype, ix->sm_count, queries_dev, B, 10, uint32_t(row_begin),
                        uint32_t(row_end), 0, nullptr, nullptr, static_cast<uint8_t*>(workspace_dev),
                        static_cast<cudaStream_t>(stream), g_err, out_scores_dev, out_ld);

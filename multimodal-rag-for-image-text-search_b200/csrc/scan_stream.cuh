@@ -41,6 +41,7 @@ constexpr int K1_NW = MMR_K1_NW;   // consumer warps per CTA
 constexpr int K1_THREADS = K1_NW * 32;
 constexpr int MMR_MAX_PEERS = 16;
 
+constexpr int MMR_MAX_K_DEVICE = 64;  // == MMR_MAX_K (include/mmr_b200.h)
 constexpr int K1_ITEM_NQ = 4;        // queries per varlen work item (one pass over the item's rows serves all of them)
 constexpr int K1_INLINE_FLOATS = 1024;  // queries that ride in the kernel parameters (2 x 512 floats)
 
@@ -448,6 +449,119 @@ __global__ void __launch_bounds__(K1_THREADS, 1) scan_stream_kernel(const __grid
 #pragma unroll
       for (int qi = 0; qi < NQ; ++qi)
         if (qi < nq_live) list[qi].store(p.partial + (size_t(it) * NQ + qi) * k, k, lane);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact rescoring of tensor-core candidates (query precision policy MMR_QP_RESCORE).
+// K2 scores rows against the 16-bit rounding of the query; a serving store must not let a request's answer depend on
+// whether it was batched onto the tensor cores.  So K2 only NOMINATES: it returns kc > k candidates per query, this
+// kernel re-scores them with the fp32 query using EXACTLY K1's arithmetic (same lane <-> element mapping, same fmaf
+// order, same butterfly; the functions below are the ones K1's inner loop is written from), keeps the best k, and
+// proves the answer equal to K1's:  every row K2 did not nominate has a 16-bit score <= c_min (the kc-th candidate's),
+// hence an fp32 score <= c_min + eps with eps >= |s32 - s16| for any row (eps = 1.01 ||q - q16|| + 2e-5, Cauchy-
+// Schwarz on unit rows).  If the k-th rescored score is above that, no outsider can belong to the top-k.  Otherwise
+// (rare: it needs the candidates' scores packed inside ~1e-3) the query is flagged and the host reruns it on K1.
+// ------------------------------------------------------------------------------------------------
+template <typename E, int D>
+__device__ __forceinline__ void k1_load_unit_query(const float* __restrict__ qsrc, int lane, float (&q)[D / 32]) {
+  using C = StreamCfg<E, D, 1, 1>;
+  float ss = 0.f;
+#pragma unroll
+  for (int t = 0; t < C::NV; ++t)
+#pragma unroll
+    for (int j = 0; j < C::RPV * C::EPR; ++j) {
+      const float x = qsrc[(t * 32 + lane) * (C::RPV * C::EPR) + j];
+      q[t * C::RPV * C::EPR + j] = x;
+      ss += x * x;
+    }
+  ss = warp_allreduce_sum(ss);
+  const float nrm = sqrtf(ss);
+  if (nrm > 0.f) {
+#pragma unroll
+    for (int e = 0; e < C::EPL; ++e) q[e] = q[e] / nrm;
+  }
+}
+
+template <typename E, int D>
+__device__ __forceinline__ float k1_row_score(const uint8_t* __restrict__ row, const float (&q)[D / 32], int lane) {
+  using C = StreamCfg<E, D, 1, 1>;
+  float acc = 0.f;
+#pragma unroll
+  for (int t = 0; t < C::NV; ++t) {
+    uint32_t w[C::RPV];
+    const uint8_t* src = row + lane * C::VECB + t * (32 * C::VECB);
+    if constexpr (C::VECB == 16) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
+      w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    } else {
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(src));
+      w[0] = v.x; w[1] = v.y;
+    }
+#pragma unroll
+    for (int j = 0; j < C::RPV; ++j) {
+      if constexpr (C::EB == 2) {
+        float a, b;
+        ElemTraits<E>::unpack(w[j], a, b);
+        acc = fmaf(a, q[(t * C::RPV + j) * 2 + 0], acc);
+        acc = fmaf(b, q[(t * C::RPV + j) * 2 + 1], acc);
+      } else {
+        acc = fmaf(__uint_as_float(w[j]), q[t * C::RPV + j], acc);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);   // K1's butterfly: offsets 16, 8, 4, 2, 1
+  return acc;
+}
+
+// one CTA (8 warps) per query: candidates [B, kc] (16-bit-query scores + GLOBAL row ids as written by K2's merge) ->
+// exact top-k [B, k] + flag[b] (1 = proven exact, 0 = rerun on K1)
+template <typename E, int D, int KPL>
+__global__ void __launch_bounds__(256) rescore_kernel(const void* __restrict__ rows, const float* __restrict__ queries,
+                                                      const float* __restrict__ cand_scores, const int64_t* __restrict__ cand_rows,
+                                                      const float* __restrict__ qerr, int kc, int k, int64_t row_base,
+                                                      float* __restrict__ out_scores, int64_t* __restrict__ out_rows,
+                                                      uint8_t* __restrict__ exact_flag) {
+  __shared__ uint64_t keys[MMR_MAX_K_DEVICE];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float q[D / 32];
+  k1_load_unit_query<E, D>(queries + size_t(b) * D, lane, q);
+  const uint8_t* rows8 = reinterpret_cast<const uint8_t*>(rows);
+  for (int c = warp; c < kc; c += 8) {
+    const int64_t r = cand_rows[size_t(b) * kc + c];
+    uint64_t key = 0ull;
+    if (r >= 0) {
+      const uint32_t local = uint32_t(r - row_base);
+      const float s = k1_row_score<E, D>(rows8 + size_t(local) * (D * sizeof(E)), q, lane);
+      key = make_key(s, local);
+    }
+    if (lane == 0) keys[c] = key;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    WarpTopK<KPL> m;
+    m.clear();
+    uint64_t thr = 0ull;
+    thr = m.template merge_batched<2>([&](int i) -> uint64_t { return keys[i]; }, kc, thr, k, lane);
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+      const int pos = j * 32 + lane;
+      if (pos < k) {
+        const uint64_t key = m.key[j];
+        out_scores[size_t(b) * k + pos] = key ? key_score(key) : -INFINITY;
+        out_rows[size_t(b) * k + pos] = key ? int64_t(key_row(key)) + row_base : int64_t(-1);
+      }
+    }
+    if (lane == 0) {
+      // candidates are sorted best-first by K2's merge: the last VALID one carries c_min; fewer than kc valid candidates
+      // means K2 nominated every row of the range
+      const bool all_rows = cand_rows[size_t(b) * kc + kc - 1] < 0;
+      const float c_min = cand_scores[size_t(b) * kc + kc - 1];
+      const float eps = 1.01f * qerr[b] + 2e-5f;
+      const float kth32 = thr ? key_score(thr) : -INFINITY;      // k-th best rescored score (thr = k-th key, 0 if < k hits)
+      exact_flag[b] = (all_rows || (thr != 0ull && kth32 > c_min + eps)) ? 1 : 0;
     }
   }
 }

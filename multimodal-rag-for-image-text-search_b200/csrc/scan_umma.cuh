@@ -500,7 +500,8 @@ __global__ void probe_floor_kernel(const float* __restrict__ probe, int n_qtiles
 
 // fp32 queries -> L2-normalised bf16 (LanceDBStore._normalize, then narrowed for the tensor cores). Warp per query.
 template <typename E>
-__global__ void prep_queries_kernel(const float* __restrict__ q, E* __restrict__ out, int B, int dim) {
+__global__ void prep_queries_kernel(const float* __restrict__ q, E* __restrict__ out, int B, int dim,
+                                    float* __restrict__ qerr = nullptr) {
   pdl_chain_prologue();
   const int lane = threadIdx.x & 31;
   const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -510,10 +511,26 @@ __global__ void prep_queries_kernel(const float* __restrict__ q, E* __restrict__
   for (int i = lane; i < dim; i += 32) ss = fmaf(s[i], s[i], ss);
   ss = warp_allreduce_sum(ss);
   const float nrm = sqrtf(ss);
+  float err2 = 0.f;
   for (int i = lane; i < dim; i += 32) {
     const float x = nrm > 0.f ? s[i] / nrm : s[i];
-    if constexpr (sizeof(E) == 2 && std::is_same<E, __half>::value) out[size_t(qi) * dim + i] = __float2half_rn(x);
-    else out[size_t(qi) * dim + i] = __float2bfloat16_rn(x);
+    float back;
+    if constexpr (sizeof(E) == 2 && std::is_same<E, __half>::value) {
+      const __half h = __float2half_rn(x);
+      out[size_t(qi) * dim + i] = h;
+      back = __half2float(h);
+    } else {
+      const __nv_bfloat16 h = __float2bfloat16_rn(x);
+      out[size_t(qi) * dim + i] = h;
+      back = __bfloat162float(h);
+    }
+    err2 = fmaf(x - back, x - back, err2);
+  }
+  // ||q_unit - q_16bit||_2: bounds how far the tensor-core score of ANY unit row can be from its fp32-query score
+  // (Cauchy-Schwarz); used by the rescoring mode to prove its result exact
+  if (qerr != nullptr) {
+    err2 = warp_allreduce_sum(err2);
+    if (lane == 0) qerr[qi] = sqrtf(err2);
   }
 }
 #endif  // __CUDACC__

@@ -387,7 +387,7 @@ struct Umma2IndexState {
 inline int umma_search(UmmaIndexState& st, Umma2IndexState& st2, const void* rows, int64_t n_rows, int dim, int dtype, int sm_count,
                        const float* queries, int B, int k, uint32_t r0, uint32_t r1, int64_t row_base, float* out_s,
                        int64_t* out_r, uint8_t* ws, cudaStream_t stream, std::string& err, float* dump = nullptr,
-                       int64_t dump_ld = 0) {
+                       int64_t dump_ld = 0, float* qerr = nullptr) {
   if (!st.valid || st.rows != rows || st.n_rows != n_rows) {
     if (!umma_make_map(&st.map, rows, n_rows, dim, dtype == MMR_BF16)) {
       err = "cuTensorMapEncodeTiled failed for the index";
@@ -446,8 +446,8 @@ inline int umma_search(UmmaIndexState& st, Umma2IndexState& st2, const void* row
   float* floor = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(probe) + umma_align(size_t(ctas_max) * K2_BM * 4));
   uint32_t* progress = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(floor) + umma_align(size_t(B) * 4));
   const bool noprobe = options().umma_noprobe != 0;
-  if (dtype == MMR_BF16) launch_pdl(prep_queries_kernel<__nv_bfloat16>, dim3((B + 3) / 4), dim3(128), 0, stream, queries, qb, B, dim);
-  else launch_pdl(prep_queries_kernel<__half>, dim3((B + 3) / 4), dim3(128), 0, stream, queries, reinterpret_cast<__half*>(qb), B, dim);
+  if (dtype == MMR_BF16) launch_pdl(prep_queries_kernel<__nv_bfloat16>, dim3((B + 3) / 4), dim3(128), 0, stream, queries, qb, B, dim, qerr);
+  else launch_pdl(prep_queries_kernel<__half>, dim3((B + 3) / 4), dim3(128), 0, stream, queries, reinterpret_cast<__half*>(qb), B, dim, qerr);
   const int max_q_per_pass = sm_count * K2_BM;
   for (int q0 = 0; q0 < B; q0 += max_q_per_pass) {
     const int bq = std::min(B - q0, max_q_per_pass);

@@ -175,8 +175,11 @@ class ResidentIndex:
 
     def set_query_precision(self, mode: str) -> None:
         """"auto": batches of >= 3 queries on one row range use the tensor-core kernels (16-bit queries);
-        "f32": every query is scored in fp32, so a request's result never depends on its batch (serving default)."""
-        N.check(N.lib().mmr_index_set_query_precision(self._handle, {"auto": N.MMR_QP_AUTO, "f32": N.MMR_QP_F32}[mode]))
+        "f32": every query is scored in fp32 (K1 passes), so a request's result never depends on its batch;
+        "rescore": tensor-core candidates re-scored in fp32 with K1's arithmetic and proven exact -- the same
+        batch-independent, bit-identical results at tensor-core throughput (serving default of B200Store)."""
+        N.check(N.lib().mmr_index_set_query_precision(
+            self._handle, {"auto": N.MMR_QP_AUTO, "f32": N.MMR_QP_F32, "rescore": N.MMR_QP_RESCORE}[mode]))
 
     def search(self, queries: torch.Tensor, k: int, segments: Optional[Sequence[int]] = None,
                out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -438,7 +438,7 @@ class B200Store:
     """
 
     def __init__(self, db_path: Optional[str] = None, device: Any = "cuda:0", dtype: str = "bf16",
-                 devices: Optional[Sequence[Any]] = None, query_precision: str = "f32") -> None:
+                 devices: Optional[Sequence[Any]] = None, query_precision: str = "rescore") -> None:
         """devices=[0, 1, ..., 7]: row-range-shard every collection over those GPUs of this box (one process; the same
         search_* calls; results bit-identical to one GPU).  query_precision: see _Collection."""
         N.lib()  # fail now, loudly, if the CUDA library is missing
@@ -448,7 +448,7 @@ class B200Store:
         self._init_state(db_path, devs[0] if devs else torch.device(device), dtype, devs, query_precision)
 
     def _init_state(self, db_path: Optional[str], device: torch.device, dtype: str, devices=None,
-                    query_precision: str = "f32") -> None:
+                    query_precision: str = "rescore") -> None:
         self._device = device
         self._db_path = db_path
         if db_path:

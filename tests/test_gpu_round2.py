@@ -63,6 +63,34 @@ def test_precision_policy_f32_keeps_batches_bit_identical(mmr, table):
     assert (s2 - s).abs().max().item() < util.TOL_BF16
 
 
+def test_rescore_policy_is_bit_identical_to_single_queries_on_the_tensor_cores(mmr, table):
+    """The serving default: tensor-core candidates + fp32 re-scoring in K1's arithmetic + an exactness proof (rerun on K1
+    when it fails).  Same-tenant batches then run on the tensor cores AND equal the single-query results bit for bit."""
+    rows, seg, ix = table
+    lib = mmr._native.lib()
+    ix.set_query_precision("rescore")
+    try:
+        for tenant, b, k in ((4, 9, 10), (4, 130, 12), (2, 40, 50), (-1, 300, 10), (0, 5, 10), (3, 4, 3), (5, 7, 64)):
+            q = torch.from_numpy(util.queries(b, 512, seed=400 + b)).cuda()
+            q[1] = q[0] * 3.0                                    # not unit norm: re-normalised on the device
+            s, r = ix.search(q, k, [tenant] * b)
+            assert lib.mmr_last_kernel() == 2, (tenant, b, k)
+            ix.set_query_precision("f32")
+            for j in range(0, b, max(1, b // 12)):
+                s1, r1 = ix.search(q[j:j + 1], k, [tenant])
+                assert torch.equal(r[j], r1[0]) and torch.equal(s[j], s1[0]), (tenant, b, k, j)
+            ix.set_query_precision("rescore")
+        # duplicates: exact ties between a nominated and a non-nominated row cannot flip the order
+        q = torch.from_numpy(np.repeat(rows[40_000:40_001], 6, axis=0)).cuda()
+        s, r = ix.search(q, 10, [4] * 6)
+        ix.set_query_precision("f32")
+        s1, r1 = ix.search(q[:1], 10, [4])
+        assert torch.equal(r[3], r1[0]) and torch.equal(s[3], s1[0]) and int(r[3, 0]) == 40_000
+        print("rescore reruns so far:", lib.mmr_rescore_reruns())
+    finally:
+        ix.set_query_precision("auto")
+
+
 def test_store_same_tenant_batch_equals_per_request(mmr):
     """Through the drop-in: 6 requests of one tenant in one micro-batch == the 6 requests served alone, dict for dict."""
     rng = np.random.default_rng(304)
