@@ -441,12 +441,18 @@ __global__ void clip_head_kernel(const float* __restrict__ x, const int32_t* __r
   // projection: warp w computes outputs w, w + nwarps, ... with coalesced reads of the weight rows
   float* proj_out = head_smem + H;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int o = warp; o < P; o += nwarps) {
-    const float* w = proj + size_t(o) * H;
-    float a = 0.f;
-    for (int i = lane; i < H; i += 32) a = fmaf(w[i], head_smem[i], a);
-    a = warp_allreduce_sum(a);
-    if (lane == 0) proj_out[o] = a;
+  for (int o0 = warp * 4; o0 < P; o0 += nwarps * 4) {   // 4 weight rows per warp in flight
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = lane; i < H; i += 32) {
+      const float xv = head_smem[i];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a[u] = fmaf(proj[size_t(min(o0 + u, P - 1)) * H + i], xv, a[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float t = warp_allreduce_sum(a[u]);
+      if (lane == 0 && o0 + u < P) proj_out[o0 + u] = t;
+    }
   }
   __syncthreads();
   const float e = c < P ? proj_out[c] : 0.f;
@@ -466,12 +472,18 @@ __global__ void cross_head_kernel(const float* __restrict__ x, int S, int H, con
   __syncthreads();
   float* pooled = head_smem + H;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int o = warp; o < H; o += nwarps) {     // coalesced reads of the pooler's weight rows
-    const float* w = pool_w + size_t(o) * H;
-    float a = 0.f;
-    for (int i = lane; i < H; i += 32) a = fmaf(w[i], head_smem[i], a);
-    a = warp_allreduce_sum(a);
-    if (lane == 0) pooled[o] = tanhf(a + pool_b[o]);
+  for (int o0 = warp * 4; o0 < H; o0 += nwarps * 4) {   // 4 weight rows per warp in flight, coalesced reads
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = lane; i < H; i += 32) {
+      const float xv = head_smem[i];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a[u] = fmaf(pool_w[size_t(min(o0 + u, H - 1)) * H + i], xv, a[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float t = warp_allreduce_sum(a[u]);
+      if (lane == 0 && o0 + u < H) pooled[o0 + u] = tanhf(t + pool_b[o0 + u]);
+    }
   }
   __syncthreads();
   const float logit = block_sum(pooled[c] * cls_w[c], red);
