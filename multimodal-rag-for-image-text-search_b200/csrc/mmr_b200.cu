@@ -104,6 +104,7 @@ static int* option_slot(const char* name) {
   if (!strcmp(name, "MMR_UMMA_NOPROBE")) return &o.umma_noprobe;
   if (!strcmp(name, "MMR_FORCE_FAMILY")) return &o.force_family;
   if (!strcmp(name, "MMR_UMMA_LOCKSTEP")) return &o.umma_lockstep;
+  if (!strcmp(name, "MMR_UMMA_SKIP_EPI")) return &o.umma_skip_epi;
   if (!strcmp(name, "MMR_INLINE_QUERY")) return &o.inline_query;
   if (!strcmp(name, "MMR_MAILBOX")) return &o.mailbox;
   return nullptr;
@@ -114,7 +115,7 @@ static int parse_option(const char* name, const char* v, int dflt) {
   return atoi(v);
 }
 static const char* kOptionNames[] = {"MMR_PDL", "MMR_UMMA_MODE", "MMR_UMMA_PAIR", "MMR_UMMA_NOPROBE", "MMR_FORCE_FAMILY",
-                                     "MMR_UMMA_LOCKSTEP", "MMR_INLINE_QUERY", "MMR_MAILBOX"};
+                                     "MMR_UMMA_LOCKSTEP", "MMR_INLINE_QUERY", "MMR_MAILBOX", "MMR_UMMA_SKIP_EPI"};
 namespace {
 struct OptionsFromEnv {  // the environment is read once, when the library is loaded
   OptionsFromEnv() {
@@ -583,15 +584,19 @@ static int search_varlen_stream(const mmr_index* ix, const float* q, const std::
   const int64_t target = int64_t(twarps) * VARLEN_ITEMS_PER_WARP;
   int64_t item_rows = std::max<int64_t>(64, (total_rows + target - 1) / target);
   item_rows = (item_rows + R - 1) / R * R;
-  // 3. emit items and per-query slots
-  std::vector<ScanItem> items;
+  // 3. emit items and per-query slots.  Two classes: items of single-query groups (run by the NQ = 1 instantiation, which
+  //    streams at the HBM roofline) and items of 2..4-query groups (NQ = 4: four dot products per row byte, FMA-paced
+  //    at ~5.5 TB/s) -- a batch that mostly hits distinct tenants must not pay the 4-query arithmetic on every row.
+  std::vector<ScanItem> items, items_multi;
   std::vector<QuerySlot> slots(B);
+  std::vector<std::pair<int, int>> multi_slots;   // (query, first item inside items_multi) fixed up after concatenation
   items.reserve(size_t(std::min<int64_t>(target + n_group_ranges, 1 << 22)));
   for (size_t t = 0; t < members.size(); ++t) {
     const std::vector<int>& m = members[t];
     for (size_t g0 = 0; g0 < m.size(); g0 += K1_ITEM_NQ) {
       const int nq = int(std::min<size_t>(K1_ITEM_NQ, m.size() - g0));
-      const int item0 = int(items.size());
+      std::vector<ScanItem>& dst = nq == 1 ? items : items_multi;
+      const int item0 = int(dst.size());
       for (auto& r : *tenant_ranges[t]) {
         for (int64_t s = r.first; s < int64_t(r.second); s += item_rows) {
           ScanItem it;
@@ -600,12 +605,18 @@ static int search_varlen_stream(const mmr_index* ix, const float* q, const std::
           for (int j = 0; j < K1_ITEM_NQ; ++j) it.query[j] = m[g0 + std::min(j, nq - 1)];
           it.nq = nq;
           it.pad = 0;
-          items.push_back(it);
+          dst.push_back(it);
         }
       }
-      for (int j = 0; j < nq; ++j) slots[m[g0 + j]] = QuerySlot{item0, int(items.size()) - item0, j, 0};
+      for (int j = 0; j < nq; ++j) {
+        slots[m[g0 + j]] = QuerySlot{item0, int(dst.size()) - item0, j, 0};
+        if (nq > 1) multi_slots.push_back({m[g0 + j], item0});
+      }
     }
   }
+  const int n_single = int(items.size());
+  for (auto& ms : multi_slots) slots[ms.first].item0 = n_single + ms.second;
+  items.insert(items.end(), items_multi.begin(), items_multi.end());
   const int n_items = int(items.size());
   const size_t part_bytes = align_up(size_t(std::max(n_items, 1)) * K1_ITEM_NQ * k * 8, 256);
   const size_t item_bytes = align_up(size_t(std::max(n_items, 1)) * sizeof(ScanItem), 256);
@@ -621,20 +632,25 @@ static int search_varlen_stream(const mmr_index* ix, const float* q, const std::
   // pageable sources: cudaMemcpyAsync stages them before returning, the vectors may die after this call
   if (n_items > 0) CUDA_TRY(cudaMemcpyAsync(d_items, items.data(), size_t(n_items) * sizeof(ScanItem), cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(d_slots, slots.data(), size_t(B) * sizeof(QuerySlot), cudaMemcpyHostToDevice, st));
-  if (n_items > 0) {
+  for (int cls = 0; cls < 2; ++cls) {
+    const int first = cls == 0 ? 0 : n_single;
+    const int count = cls == 0 ? n_single : n_items - n_single;
+    if (count <= 0) continue;
+    const int nq_launch = cls == 0 ? 1 : K1_ITEM_NQ;
     StreamParams p;
     memset(&p, 0, offsetof(StreamParams, qinline));
     p.rows = ix->rows;
     p.queries = q;
-    p.nq = K1_ITEM_NQ;
+    p.nq = nq_launch;
     p.k = k;
-    p.partial = d_part;
+    p.partial = d_part + size_t(first) * K1_ITEM_NQ * k;
     p.ticket = reinterpret_cast<unsigned int*>(ws);
     p.row_base = ix->row_base;
-    p.items = d_items;
-    p.n_items = n_items;
-    const int grid = int(std::min<int64_t>(ix->sm_count, (n_items + K1_NW - 1) / K1_NW));
-    int rc = launch_stream(ix, p, K1_ITEM_NQ, kpl, grid, st);
+    p.items = d_items + first;
+    p.n_items = count;
+    p.item_nq = K1_ITEM_NQ;
+    const int grid = int(std::min<int64_t>(ix->sm_count, (count + K1_NW - 1) / K1_NW));
+    int rc = launch_stream(ix, p, nq_launch, kpl, grid, st);
     if (rc != MMR_OK) return rc;
   }
   const int wpb = 4;

@@ -75,6 +75,7 @@ struct StreamParams {
   int64_t row_base;             // shard base added to the int64 row ids written out
   const ScanItem* items;        // varlen mode (nullptr = uniform)
   int32_t n_items;
+  int32_t item_nq;              // varlen mode: lists per item in `partial` (K1_ITEM_NQ, whatever NQ this launch runs with)
   // Fused exchange (row-range shards over NVLink): the last CTA also stores the final [B, k] result straight into
   // every peer's symmetric buffer (this rank's slot) and then releases that peer's flag with `seq`.
   int32_t n_peers;              // 0 = no exchange
@@ -448,7 +449,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) scan_stream_kernel(const __grid
       scan_range(item.row_begin, item.row_end, 0, 1);
 #pragma unroll
       for (int qi = 0; qi < NQ; ++qi)
-        if (qi < nq_live) list[qi].store(p.partial + (size_t(it) * NQ + qi) * k, k, lane);
+        if (qi < nq_live) list[qi].store(p.partial + (size_t(it) * p.item_nq + qi) * k, k, lane);
     }
   }
 }

@@ -59,6 +59,7 @@ struct UmmaParams {
   // read the same index tiles within an L2-resident window, so each tile is fetched from HBM once (it was 1.5-2x).
   uint32_t* progress;
   int32_t window;
+  int32_t skip_epi;   // measurement only: epilogue hands accumulators back without reading them
 };
 
 #ifdef __CUDACC__

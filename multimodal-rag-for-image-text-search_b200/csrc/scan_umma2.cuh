@@ -280,7 +280,7 @@ scan_umma2_kernel(const __grid_constant__ CUtensorMap tm_x, const UmmaParams p) 
       const int nvalid = int(min(uint32_t(K2_NT), p.row_end - row0));
       mbar_wait(bar_tfull + acc * 8, acc_phase);
       tc_fence_after();
-      if (warp_live) {
+      if (warp_live && !p.skip_epi) {
 #pragma unroll 1
         for (int c = 0; c < K2_NT / 32; ++c) {
           uint32_t v[32];
@@ -488,6 +488,7 @@ inline int umma_search(UmmaIndexState& st, Umma2IndexState& st2, const void* row
     p.qbf16 = qb + size_t(q0) * dim;
     p.dump = dump ? dump + int64_t(q0) * dump_ld : nullptr;
     p.dump_ld = dump_ld;
+    p.skip_epi = options().umma_skip_epi;
     const int grid = pair ? 2 * n_qpairs * p.n_rslots : p.n_qtiles * p.n_rslots;
     // probe pass: worth it when every CTA streams many tiles (the warm-up it removes is ~k ln(n/k) inserts/thread)
     const int64_t tiles_per_cta = ntiles / p.n_rslots;
