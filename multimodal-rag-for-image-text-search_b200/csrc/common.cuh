@@ -164,6 +164,12 @@ __device__ __forceinline__ void pdl_chain_prologue() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// The two halves separately: a kernel whose first phase touches nothing its predecessor wrote (barrier init, tensor-memory
+// allocation, TMA loads of the index) lets that phase run UNDER the predecessor and waits only in the warps that read the
+// predecessor's outputs.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

@@ -24,10 +24,11 @@ namespace mmr {
 
 constexpr int ENC_THREADS = 192;
 constexpr int ENC_BM = 128;   // output features per tile (UMMA M)
-constexpr int ENC_NT = 64;    // tokens per tile (UMMA N)
 constexpr int ENC_W_SLICE = ENC_BM * 128;  // 16 KB: [128 features x 64 bf16]
-constexpr int ENC_X_SLICE = ENC_NT * 128;  //  8 KB: [64 tokens   x 64 bf16]
 constexpr int ENC_MAX_STAGES = 8;
+// tokens per tile (UMMA N) is a template parameter NT in {64, 128, 256}: a single query (16 tokens) wants many small CTAs,
+// a micro-batch of 128 queries or 64 rerank pairs (2k-8k tokens) wants fewer, larger ones (per-CTA setup amortised, weight
+// tile re-read less often)
 
 enum GemmEpilogue { EPI_BIAS_F32 = 0, EPI_BIAS_RES_F32 = 1, EPI_GELU_BF16 = 2, EPI_QUICKGELU_BF16 = 3 };
 
@@ -41,8 +42,8 @@ struct GemmParams {
 };
 
 #ifdef __CUDACC__
-__host__ __device__ constexpr uint32_t enc_idesc() {  // kind::f16, bf16 x bf16 -> f32, M = 128, N = 64, both K-major
-  return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(ENC_NT >> 3) << 17) | (uint32_t(ENC_BM >> 4) << 24);
+__host__ __device__ constexpr uint32_t enc_idesc(int nt) {  // kind::f16, bf16 x bf16 -> f32, M = 128, N = nt, both K-major
+  return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(nt >> 3) << 17) | (uint32_t(ENC_BM >> 4) << 24);
 }
 __device__ __forceinline__ void tmem_alloc_cols(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
@@ -54,18 +55,21 @@ __device__ __forceinline__ void tmem_dealloc_cols(uint32_t taddr, uint32_t ncols
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
 
-// out[t, f] = epilogue( sum_k X[t, k] * W[f, k] + bias[f] )      grid = (N / 128, ceil(M / 64))
-template <int EPI>
+// out[t, f] = epilogue( sum_k X[t, k] * W[f, k] + bias[f] )      grid = (N / 128, ceil(M / NT))
+template <int EPI, int NT>
 __global__ void __launch_bounds__(ENC_THREADS, 1)
 gemm_wt_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x, const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  pdl_chain_prologue();
+  pdl_launch_dependents();   // barrier init / tensor-memory allocation run under the previous kernel of the forward pass;
+                             // the producer (activations) and the epilogue (residual, outputs) wait for it below
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nst = p.nstages;
   const int ks = p.K / 64;
+  constexpr int ENC_NT = NT;
+  constexpr int ENC_X_SLICE = NT * 128;                             // [NT tokens x 64 bf16]
   const uint32_t w_s = smem_u32(smem);                              // [nst][16 KB]
-  const uint32_t x_s = w_s + uint32_t(nst) * ENC_W_SLICE;           // [nst][ 8 KB]
+  const uint32_t x_s = w_s + uint32_t(nst) * ENC_W_SLICE;           // [nst][NT * 128 B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(nst) * (ENC_W_SLICE + ENC_X_SLICE));
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = bar_full + ENC_MAX_STAGES * 8;
@@ -95,6 +99,7 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
     const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
+    pdl_wait_prior_grid();   // the activation tile is the previous kernel's output
     for (int s = 0; s < ks; ++s) {
       mbar_wait(bar_empty + stage * 8, phase ^ 1u);
       if (leader) {
@@ -110,7 +115,7 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
     }
   } else if (warp == 1) {
     const bool leader = elect_one();
-    const uint32_t idesc = enc_idesc();
+    const uint32_t idesc = enc_idesc(NT);
     int stage = 0;
     uint32_t phase = 0;
     for (int s = 0; s < ks; ++s) {
@@ -137,6 +142,7 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
     const int quarter = warp & 3;
     const int f = f0 + quarter * 32 + lane;
     const float b = p.bias ? p.bias[f] : 0.f;
+    pdl_wait_prior_grid();   // residual / output buffers belong to the chain
     mbar_wait(bar_acc, 0);
     tc_fence_after();
 #pragma unroll 1

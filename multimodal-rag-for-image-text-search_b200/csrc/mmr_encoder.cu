@@ -217,9 +217,11 @@ static int ensure_arena(mmr_encoder* e, int tokens, int seqs) {
   return MMR_OK;
 }
 
-template <int EPI>
-static int launch_gemm(const CUtensorMap& mw, const CUtensorMap& mx, int M, int N, int K, const float* bias,
-                       const float* residual, float* out_f32, __nv_bfloat16* out_bf16, cudaStream_t st) {
+static int enc_token_tile(int M) { return M <= 1024 ? 64 : (M <= 4096 ? 128 : 256); }
+
+template <int EPI, int NT>
+static int launch_gemm_nt(const CUtensorMap& mw, const CUtensorMap& mx, int M, int N, int K, const float* bias,
+                          const float* residual, float* out_f32, __nv_bfloat16* out_bf16, cudaStream_t st) {
   static bool attr_done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -227,20 +229,30 @@ static int launch_gemm(const CUtensorMap& mw, const CUtensorMap& mx, int M, int 
   p.M = M;
   p.N = N;
   p.K = K;
-  p.nstages = std::min(ENC_MAX_STAGES, K / 64);
+  const int stage_bytes = ENC_W_SLICE + NT * 128;
+  p.nstages = std::min(std::min(ENC_MAX_STAGES, K / 64), (200 * 1024) / stage_bytes);
   p.bias = bias;
   p.residual = residual;
   p.out_f32 = out_f32;
   p.out_bf16 = out_bf16;
-  const size_t smem = size_t(p.nstages) * (ENC_W_SLICE + ENC_X_SLICE) + (2 * ENC_MAX_STAGES + 2) * 8 + 64;
+  const size_t smem = size_t(p.nstages) * stage_bytes + (2 * ENC_MAX_STAGES + 2) * 8 + 64;
   if (!attr_done[dev & 63]) {
-    CUDA_TRY(cudaFuncSetAttribute(gemm_wt_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  ENC_MAX_STAGES * (ENC_W_SLICE + ENC_X_SLICE) + 1024));
+    CUDA_TRY(cudaFuncSetAttribute(gemm_wt_kernel<EPI, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     attr_done[dev & 63] = true;
   }
-  CUDA_TRY(launch_pdl(gemm_wt_kernel<EPI>, dim3(N / ENC_BM, (M + ENC_NT - 1) / ENC_NT), dim3(ENC_THREADS), smem, st, mw, mx, p));
+  CUDA_TRY(launch_pdl(gemm_wt_kernel<EPI, NT>, dim3(N / ENC_BM, (M + NT - 1) / NT), dim3(ENC_THREADS), smem, st, mw, mx, p));
   mmr_g_launches++;
   return MMR_OK;
+}
+
+template <int EPI>
+static int launch_gemm(const CUtensorMap& mw, const CUtensorMap& mx, int M, int N, int K, const float* bias,
+                       const float* residual, float* out_f32, __nv_bfloat16* out_bf16, cudaStream_t st) {
+  switch (enc_token_tile(M)) {
+    case 64: return launch_gemm_nt<EPI, 64>(mw, mx, M, N, K, bias, residual, out_f32, out_bf16, st);
+    case 128: return launch_gemm_nt<EPI, 128>(mw, mx, M, N, K, bias, residual, out_f32, out_bf16, st);
+    default: return launch_gemm_nt<EPI, 256>(mw, mx, M, N, K, bias, residual, out_f32, out_bf16, st);
+  }
 }
 
 template <int H>
@@ -251,8 +263,9 @@ static int forward_t(mmr_encoder* e, int B, int S, float* out_dev, cudaStream_t 
   const int wpb = 8;
   const dim3 rows_grid((M + wpb - 1) / wpb), rows_block(wpb * 32);
   if (e->maps_tokens != M) {   // the activation maps depend on the live token count (TMA zero-fills rows past it)
-    if (!make_map(&e->m_x16, e->x16, M, H, ENC_NT) || !make_map(&e->m_ctx16, e->ctx16, M, H, ENC_NT) ||
-        !make_map(&e->m_h16, e->h16, M, I, ENC_NT))
+    const int nt = enc_token_tile(M);   // box rows of the activation maps = the GEMMs' token tile
+    if (!make_map(&e->m_x16, e->x16, M, H, nt) || !make_map(&e->m_ctx16, e->ctx16, M, H, nt) ||
+        !make_map(&e->m_h16, e->h16, M, I, nt))
       return fail(MMR_ERR_CUDA, "cuTensorMapEncodeTiled failed for the activations");
     e->maps_tokens = M;
   }

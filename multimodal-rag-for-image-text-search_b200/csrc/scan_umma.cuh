@@ -198,7 +198,10 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
 scan_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x,
                  const UmmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  pdl_chain_prologue();
+  // Programmatic dependent launch: setup, tensor-memory allocation and the first index tiles run under the previous kernel
+  // of the chain (prep / floor); only the warps that read what it wrote (queries, floors) or that write buffers it may
+  // still read (partials, probe maxima) wait for it -- see the pdl_wait_prior_grid() calls below.
+  pdl_launch_dependents();
   constexpr int NACC = TS ? 2 : K2_ACC;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -252,6 +255,7 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     // uniform lets the compiler hold addresses / coordinates in uniform registers.
     const bool leader = elect_one();
     if constexpr (!TS) {
+      pdl_wait_prior_grid();   // the query tile was written by prep_queries_kernel
       if (leader) {
         mbar_arrive_expect_tx(bar_q, uint32_t(ks) * K2_SLICE);
         for (int s = 0; s < ks; ++s) tma_load_2d(q_s + s * K2_SLICE, &tm_q, bar_q, s * 64, qt * K2_BM);
@@ -329,6 +333,7 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     const int qglob = qt * K2_BM + ql;         // query within this launch
     const bool live = qglob < p.B;
     const bool warp_live = qt * K2_BM + quarter * 32 < p.B;   // any live query in this warp
+    pdl_wait_prior_grid();     // queries / floors come from the previous kernels; partials / probe maxima may still be read
     if constexpr (TS) {
       // stage the (already normalised, bf16) query tile into tensor memory: lane = query, column c = elements 2c, 2c+1
       const uint32_t* qsrc = reinterpret_cast<const uint32_t*>(p.qbf16) + size_t(live ? qglob : 0) * (ks * 32);

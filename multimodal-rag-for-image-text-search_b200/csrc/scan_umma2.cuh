@@ -90,7 +90,7 @@ template <bool DUMP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(K2_THREADS, 1)
 scan_umma2_kernel(const __grid_constant__ CUtensorMap tm_x, const UmmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  pdl_chain_prologue();
+  pdl_launch_dependents();   // (as in scan_umma_kernel: only the epilogue warps wait for the previous kernel of the chain)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int ks = p.ks, nstages = p.nstages, k = p.k;
@@ -240,6 +240,7 @@ scan_umma2_kernel(const __grid_constant__ CUtensorMap tm_x, const UmmaParams p) 
     const bool live = qglob < p.B;
     const bool warp_live = qt * K2_BM + quarter * 32 < p.B;
     const uint32_t lead_q = mapa_u32(bar_q, 0);
+    pdl_wait_prior_grid();
     {
       const uint32_t* qsrc = reinterpret_cast<const uint32_t*>(p.qbf16) + size_t(live ? qglob : 0) * (ks * 32);
       for (int c = 0; c < ks; ++c) {

@@ -109,7 +109,7 @@ def test_cross_encoder_logits_match_fp32_torch(enc_mod):
     model = _round_linear_weights(_spread(BertForSequenceClassification(cfg)))
     enc = enc_mod.DeviceEncoder.from_hf_bert(model)
     assert enc.kind == "cross" and enc.out_dim == 1
-    for b, s in ((8, 64), (3, 300), (16, 128)):
+    for b, s in ((8, 64), (3, 300), (16, 128), (72, 64)):      # token tiles of 64, 128 and 256
         g = torch.Generator().manual_seed(s)
         ids = torch.randint(1000, 30000, (b, s), generator=g)
         lens = torch.randint(s // 2, s + 1, (b,), generator=g)
