@@ -53,6 +53,9 @@ struct Options {
   int force_family = 0;   // MMR_FORCE_FAMILY 1 = K1, 2 = K2 regardless of batch size
   int umma_lockstep = 0;      // MMR_UMMA_LOCKSTEP=1  CTA pairs of one row slot keep within a window of tiles (measured SLOWER:
                               //                      profiles/r02_k2_summary.md; kept as a measurement switch)
+  int umma_fused_probe = 0;  // MMR_UMMA_FUSED_PROBE=1  K2 single-CTA kernel: probe phase + grid barrier + floor inside the scan launch
+                             //                         instead of separate probe / floor launches (measured 22 us SLOWER at 1M rows:
+                             //                         profiles/r02_k2_summary.md; kept as a measurement switch)
   int umma_skip_epi = 0;  // MMR_UMMA_SKIP_EPI=1  K2 pair mode skips the accumulator read-back (WRONG results; measures what the
                           //                      MMA pipeline alone reaches: profiles/r02_k2_summary.md)
   int inline_query = 1;   // MMR_INLINE_QUERY=0  host-buffer calls always stage the query with an H2D copy (measurement)

@@ -105,6 +105,7 @@ static int* option_slot(const char* name) {
   if (!strcmp(name, "MMR_FORCE_FAMILY")) return &o.force_family;
   if (!strcmp(name, "MMR_UMMA_LOCKSTEP")) return &o.umma_lockstep;
   if (!strcmp(name, "MMR_UMMA_SKIP_EPI")) return &o.umma_skip_epi;
+  if (!strcmp(name, "MMR_UMMA_FUSED_PROBE")) return &o.umma_fused_probe;
   if (!strcmp(name, "MMR_INLINE_QUERY")) return &o.inline_query;
   if (!strcmp(name, "MMR_MAILBOX")) return &o.mailbox;
   return nullptr;
@@ -115,7 +116,7 @@ static int parse_option(const char* name, const char* v, int dflt) {
   return atoi(v);
 }
 static const char* kOptionNames[] = {"MMR_PDL", "MMR_UMMA_MODE", "MMR_UMMA_PAIR", "MMR_UMMA_NOPROBE", "MMR_FORCE_FAMILY",
-                                     "MMR_UMMA_LOCKSTEP", "MMR_INLINE_QUERY", "MMR_MAILBOX", "MMR_UMMA_SKIP_EPI"};
+                                     "MMR_UMMA_LOCKSTEP", "MMR_INLINE_QUERY", "MMR_MAILBOX", "MMR_UMMA_SKIP_EPI", "MMR_UMMA_FUSED_PROBE"};
 namespace {
 struct OptionsFromEnv {  // the environment is read once, when the library is loaded
   OptionsFromEnv() {
@@ -385,7 +386,7 @@ static int launch_stream_t(const StreamParams& p, int grid, cudaStream_t st) {
   // it on the same stream (the scan starts before that kernel's memory is guaranteed visible).
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(K1_THREADS);
+  cfg.blockDim = dim3(C::THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -425,19 +426,22 @@ static int launch_stream(const mmr_index* ix, const StreamParams& p, int nq_pad,
 
 // ------------------------------------------------------------------------------------------------ planning
 // Workspace layout (bytes):
-//   [0, 256)                          control block (ticket counter at +0)
+//   [0, 256)                          control block (two counters at +0: K1 arrival ticket / K6 claim + done)
 //   [256, 256 + PART)                 partial top-k keys  (uniform: grid*8*k u64; varlen: n_items*K1_ITEM_NQ*k u64)
 //   then (varlen only)                ScanItem[n_items], QuerySlot[B]
 //   last                              the K2 slice (umma_workspace_bytes)
 static constexpr size_t WS_CTRL = 256;
-static constexpr int VARLEN_ITEMS_PER_WARP = 8;
+#ifndef MMR_VARLEN_ITEMS_PER_CTA
+#define MMR_VARLEN_ITEMS_PER_CTA 8
+#endif
+static constexpr int VARLEN_ITEMS_PER_CTA = MMR_VARLEN_ITEMS_PER_CTA;   // varlen work items are per CTA (its eight warps interleave an item's chunks)
 static constexpr int RANGES_PER_QUERY_BUDGET = 8;  // = B200Store's MAX_RANGES: a tenant is compacted before it owns more
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// Upper bound of the varlen plan: ~VARLEN_ITEMS_PER_WARP pieces per warp plus one (possibly short) piece per row range.
+// Upper bound of the varlen plan: ~VARLEN_ITEMS_PER_CTA pieces per CTA plus one (possibly short) piece per row range.
 static int64_t varlen_item_cap(const mmr_index* ix, int64_t n_ranges) {
-  return int64_t(ix->sm_count) * K1_NW * VARLEN_ITEMS_PER_WARP + n_ranges + 64;
+  return int64_t(ix->sm_count) * VARLEN_ITEMS_PER_CTA + n_ranges + 64;
 }
 
 // The tensor-core slice at the END of the workspace: K2's own buffers sized for the largest k (the rescoring mode runs K2
@@ -573,29 +577,31 @@ static int search_varlen_stream(const mmr_index* ix, const float* q, const std::
     }
     members[it->second].push_back(b);
   }
-  // 2. size the pieces: about VARLEN_ITEMS_PER_WARP per warp over everything this launch reads
+  // 2. size the pieces: about VARLEN_ITEMS_PER_CTA per CTA over everything this launch reads
   int64_t total_rows = 0, n_group_ranges = 0;
   for (size_t t = 0; t < members.size(); ++t) {
     const int64_t ngroups = (int64_t(members[t].size()) + K1_ITEM_NQ - 1) / K1_ITEM_NQ;
     for (auto& r : *tenant_ranges[t]) total_rows += (int64_t(r.second) - r.first) * ngroups;
     n_group_ranges += int64_t(tenant_ranges[t]->size()) * ngroups;
   }
-  const int twarps = ix->sm_count * K1_NW;
-  const int64_t target = int64_t(twarps) * VARLEN_ITEMS_PER_WARP;
-  int64_t item_rows = std::max<int64_t>(64, (total_rows + target - 1) / target);
+  const int64_t target = int64_t(ix->sm_count) * VARLEN_ITEMS_PER_CTA;
+  int64_t item_rows = std::max<int64_t>(64 * K1_NW, (total_rows + target - 1) / target);
   item_rows = (item_rows + R - 1) / R * R;
-  // 3. emit items and per-query slots.  Two classes: items of single-query groups (run by the NQ = 1 instantiation, which
-  //    streams at the HBM roofline) and items of 2..4-query groups (NQ = 4: four dot products per row byte, FMA-paced
-  //    at ~5.5 TB/s) -- a batch that mostly hits distinct tenants must not pay the 4-query arithmetic on every row.
-  std::vector<ScanItem> items, items_multi;
+  // 3. emit items and per-query slots.  Three classes by group size -- 1 query (NQ = 1 instantiation: streams at the HBM
+  //    roofline), 2 queries (NQ = 2), 3..4 queries (NQ = 4: four dot products per row byte, the slowest stream) -- so a batch
+  //    that mostly hits distinct tenants does not pay the 4-query arithmetic on every row.
+  constexpr int N_CLS = 3;
+  static const int cls_nq[N_CLS] = {1, 2, K1_ITEM_NQ};
+  std::vector<ScanItem> cls_items[N_CLS];
   std::vector<QuerySlot> slots(B);
-  std::vector<std::pair<int, int>> multi_slots;   // (query, first item inside items_multi) fixed up after concatenation
-  items.reserve(size_t(std::min<int64_t>(target + n_group_ranges, 1 << 22)));
+  std::vector<int> slot_cls(B, 0);
+  cls_items[0].reserve(size_t(std::min<int64_t>(target + n_group_ranges, 1 << 22)));
   for (size_t t = 0; t < members.size(); ++t) {
     const std::vector<int>& m = members[t];
     for (size_t g0 = 0; g0 < m.size(); g0 += K1_ITEM_NQ) {
       const int nq = int(std::min<size_t>(K1_ITEM_NQ, m.size() - g0));
-      std::vector<ScanItem>& dst = nq == 1 ? items : items_multi;
+      const int cls = nq == 1 ? 0 : nq == 2 ? 1 : 2;
+      std::vector<ScanItem>& dst = cls_items[cls];
       const int item0 = int(dst.size());
       for (auto& r : *tenant_ranges[t]) {
         for (int64_t s = r.first; s < int64_t(r.second); s += item_rows) {
@@ -604,19 +610,29 @@ static int search_varlen_stream(const mmr_index* ix, const float* q, const std::
           it.row_end = uint32_t(std::min<int64_t>(s + item_rows, r.second));
           for (int j = 0; j < K1_ITEM_NQ; ++j) it.query[j] = m[g0 + std::min(j, nq - 1)];
           it.nq = nq;
-          it.pad = 0;
+          it.out = int(dst.size());   // list group inside its class; rebased below
           dst.push_back(it);
         }
       }
       for (int j = 0; j < nq; ++j) {
         slots[m[g0 + j]] = QuerySlot{item0, int(dst.size()) - item0, j, 0};
-        if (nq > 1) multi_slots.push_back({m[g0 + j], item0});
+        slot_cls[m[g0 + j]] = cls;
       }
     }
   }
-  const int n_single = int(items.size());
-  for (auto& ms : multi_slots) slots[ms.first].item0 = n_single + ms.second;
-  items.insert(items.end(), items_multi.begin(), items_multi.end());
+  int cls_first[N_CLS + 1] = {0};
+  for (int c = 0; c < N_CLS; ++c) cls_first[c + 1] = cls_first[c] + int(cls_items[c].size());
+  for (int b = 0; b < B; ++b) slots[b].item0 += cls_first[slot_cls[b]];
+  // launch order inside a class: largest piece first (the kernel's CTAs claim items dynamically in this order, so the
+  // launch ends on the smallest pieces); `out` keeps every item's lists where the query slots expect them
+  auto by_size = [](const ScanItem& a, const ScanItem& b) { return a.row_end - a.row_begin > b.row_end - b.row_begin; };
+  std::vector<ScanItem> items;
+  items.reserve(size_t(cls_first[N_CLS]));
+  for (int c = 0; c < N_CLS; ++c) {
+    for (auto& it : cls_items[c]) it.out += cls_first[c];
+    std::stable_sort(cls_items[c].begin(), cls_items[c].end(), by_size);
+    items.insert(items.end(), cls_items[c].begin(), cls_items[c].end());
+  }
   const int n_items = int(items.size());
   const size_t part_bytes = align_up(size_t(std::max(n_items, 1)) * K1_ITEM_NQ * k * 8, 256);
   const size_t item_bytes = align_up(size_t(std::max(n_items, 1)) * sizeof(ScanItem), 256);
@@ -632,24 +648,24 @@ static int search_varlen_stream(const mmr_index* ix, const float* q, const std::
   // pageable sources: cudaMemcpyAsync stages them before returning, the vectors may die after this call
   if (n_items > 0) CUDA_TRY(cudaMemcpyAsync(d_items, items.data(), size_t(n_items) * sizeof(ScanItem), cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(d_slots, slots.data(), size_t(B) * sizeof(QuerySlot), cudaMemcpyHostToDevice, st));
-  for (int cls = 0; cls < 2; ++cls) {
-    const int first = cls == 0 ? 0 : n_single;
-    const int count = cls == 0 ? n_single : n_items - n_single;
+  for (int cls = 0; cls < N_CLS; ++cls) {
+    const int first = cls_first[cls];
+    const int count = cls_first[cls + 1] - first;
     if (count <= 0) continue;
-    const int nq_launch = cls == 0 ? 1 : K1_ITEM_NQ;
+    const int nq_launch = cls_nq[cls];
     StreamParams p;
     memset(&p, 0, offsetof(StreamParams, qinline));
     p.rows = ix->rows;
     p.queries = q;
     p.nq = nq_launch;
     p.k = k;
-    p.partial = d_part + size_t(first) * K1_ITEM_NQ * k;
+    p.partial = d_part;   // indexed by ScanItem::out
     p.ticket = reinterpret_cast<unsigned int*>(ws);
     p.row_base = ix->row_base;
     p.items = d_items + first;
     p.n_items = count;
     p.item_nq = K1_ITEM_NQ;
-    const int grid = int(std::min<int64_t>(ix->sm_count, (count + K1_NW - 1) / K1_NW));
+    const int grid = int(std::min<int64_t>(ix->sm_count, count));
     int rc = launch_stream(ix, p, nq_launch, kpl, grid, st);
     if (rc != MMR_OK) return rc;
   }
@@ -1391,7 +1407,7 @@ extern "C" int mmr_debug_umma_scores(const mmr_index* ix, const float* queries_d
   int rc = umma_search(ix->umma, ix->umma2, ix->rows, ix->n_rows, ix->dim, ix->dtype, ix->sm_count, queries_dev, B, 10, uint32_t(row_begin),
                        uint32_t(row_end), 0, nullptr, nullptr, static_cast<uint8_t*>(workspace_dev),
                        static_cast<cudaStream_t>(stream), g_err, out_scores_dev, out_ld);
-  if (rc == MMR_OK) g_launches += 2;
+  if (rc == MMR_OK) g_launches += umma_launches_per_search();
   return rc;
 }
 #else

@@ -37,8 +37,22 @@ namespace mmr {
 #ifndef MMR_K1_ROWS
 #define MMR_K1_ROWS 4
 #endif
-constexpr int K1_NW = MMR_K1_NW;   // consumer warps per CTA
-constexpr int K1_THREADS = K1_NW * 32;
+// Groups of 2 / 4+ queries spend longer on a stage (2x / 4x the FMAs per row byte), and with two stages that compute time
+// ADDS to the copy latency instead of hiding under it (a warp's period is max(S*Tc, L + Tc) per S stages): deeper rings
+// for them.  The single-query ring stays at two stages (more bytes in flight made it slower, see above).
+#ifndef MMR_K1_STAGES_NQ2
+#define MMR_K1_STAGES_NQ2 3   // measured: K1 B = 2 on 10M rows 1.427 -> 1.394 ms, K6 2-query items 6.69 -> 6.82 TB/s
+#endif
+#ifndef MMR_K1_STAGES_NQ4
+#define MMR_K1_STAGES_NQ4 MMR_K1_STAGES
+#endif
+// Four-query groups on 16-bit rows are ISSUE-paced, not latency-paced (ncu, profiles/r02_k6_summary.md: 57 % issue-active
+// with two warps per scheduler, top stall "wait" = fixed-latency FFMA dependencies; ring depth changes nothing): they get
+// three warps per scheduler.
+#ifndef MMR_K1_NW_NQ4
+#define MMR_K1_NW_NQ4 12
+#endif
+constexpr int K1_NW = MMR_K1_NW;   // consumer warps per CTA (1- and 2-query groups, fp32 rows)
 constexpr int MMR_MAX_PEERS = 16;
 
 constexpr int MMR_MAX_K_DEVICE = 64;  // == MMR_MAX_K (include/mmr_b200.h)
@@ -50,7 +64,7 @@ struct ScanItem {  // varlen mode: one contiguous row range scanned for up to K1
   uint32_t row_end;
   int32_t query[K1_ITEM_NQ];  // query ordinals; entries >= nq are ignored
   int32_t nq;
-  int32_t pad;
+  int32_t out;                // which list group of `partial` this item writes (items are launched sorted by size)
 };
 
 struct QuerySlot {  // varlen mode: where query b's partial lists are: items [item0, item0 + n_items), list `slot` of each
@@ -69,7 +83,7 @@ struct StreamParams {
   int32_t k;
   uint32_t row_begin, row_end;  // uniform mode: the shared row range
   uint64_t* partial;            // uniform: [grid, NQ, k]; varlen: [n_items, NQ, k]
-  unsigned int* ticket;         // zero on entry, left zero on exit
+  unsigned int* ticket;         // two words, zero on entry, left zero on exit (uniform: arrival ticket; varlen: claim + done)
   float* out_scores;            // [B, k]  (uniform mode only; may be mapped host memory)
   int64_t* out_rows;            // [B, k]
   int64_t row_base;             // shard base added to the int64 row ids written out
@@ -152,23 +166,27 @@ struct StreamCfg {
   static constexpr int R = MMR_K1_ROWS;                              // rows per stage
   static constexpr int V = R * NQ;                                   // dot products per stage per warp
   static constexpr int STAGE_BYTES = R * ROW_BYTES;
-  static constexpr int S = MMR_K1_STAGES;                            // stages per warp
+  static constexpr int S_WANT = NQ >= 4 ? MMR_K1_STAGES_NQ4 : NQ >= 2 ? MMR_K1_STAGES_NQ2 : MMR_K1_STAGES;
+  static constexpr int NW = (NQ >= 4 && EB == 2) ? MMR_K1_NW_NQ4 : K1_NW;   // consumer warps per CTA
+  static constexpr int THREADS = NW * 32;
+  static constexpr int S_FIT = (160 * 1024) / (NW * STAGE_BYTES);   // fp32 rows: 8 KB stages, the ring stays <= 160 KB
+  static constexpr int S = S_WANT < S_FIT ? S_WANT : (S_FIT < 2 ? 2 : S_FIT);   // stages per warp
   static constexpr int VECB = (ROW_BYTES % 512 == 0) ? 16 : 8;       // bytes per lane per vector load
   static constexpr int NV = ROW_BYTES / (32 * VECB);                 // vector loads per lane per row
   static constexpr int RPV = VECB / 4;                               // 32-bit registers per vector
   static constexpr int EPR = 4 / EB;                                 // elements per register
   static constexpr int EPL = D / 32;                                 // elements per lane per row
   static constexpr int KSLOTS = 32 * KPL;
-  static constexpr int RING_BYTES = K1_NW * S * STAGE_BYTES;
-  static constexpr int SMEM_BYTES = RING_BYTES + K1_NW * S * 8 + 64;
+  static constexpr int RING_BYTES = NW * S * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = RING_BYTES + NW * S * 8 + 64;
   static_assert(ROW_BYTES % (32 * 8) == 0, "D * sizeof(elem) must be a multiple of 256 bytes");
   static_assert(S >= 2, "ring too shallow");
   static_assert(V <= 32, "too many dot products per stage");
-  static_assert(K1_NW * NQ * KSLOTS * 8 <= RING_BYTES, "merge scratch must fit in the ring");
+  static_assert(NW * NQ * KSLOTS * 8 <= RING_BYTES, "merge scratch must fit in the ring");
 };
 
 template <typename E, int D, int NQ, int KPL>
-__global__ void __launch_bounds__(K1_THREADS, 1) scan_stream_kernel(const __grid_constant__ StreamParams p) {
+__global__ void __launch_bounds__((StreamCfg<E, D, NQ, KPL>::THREADS), 1) scan_stream_kernel(const __grid_constant__ StreamParams p) {
   using C = StreamCfg<E, D, NQ, KPL>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::RING_BYTES);
@@ -226,8 +244,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) scan_stream_kernel(const __grid
     thr[qi] = 0ull;
   }
 
-  const int gwarp = blockIdx.x * K1_NW + warp;
-  const int twarps = gridDim.x * K1_NW;
+  const int gwarp = blockIdx.x * C::NW + warp;
+  const int twarps = gridDim.x * C::NW;
   const uint8_t* rows8 = reinterpret_cast<const uint8_t*>(p.rows);
 
   int stage = 0;          // next ring stage this warp consumes (persists across row ranges)
@@ -348,7 +366,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) scan_stream_kernel(const __grid
       uint64_t t = 0ull;
       // all heads first (position-major over the NW warp lists), so most later candidates fail the ballot
       t = m.template merge_batched<4>(
-          [&](int i) -> uint64_t { return wk[((i % K1_NW) * NQ + qi) * C::KSLOTS + i / K1_NW]; }, K1_NW * k, t, k, lane);
+          [&](int i) -> uint64_t { return wk[((i % C::NW) * NQ + qi) * C::KSLOTS + i / C::NW]; }, C::NW * k, t, k, lane);
       m.store(p.partial + (size_t(blockIdx.x) * NQ + qi) * k, k, lane);
     }
     // grid-level merge by the last CTA to arrive
@@ -369,11 +387,11 @@ __global__ void __launch_bounds__(K1_THREADS, 1) scan_stream_kernel(const __grid
       {
         // this warp's share of the per-CTA lists: parts warp, warp + NW, ...; candidates are visited position-major
         // (all heads first) so the threshold rises early, and fetched 8 per lane per round trip through L2
-        const int nmine = (nparts - warp + K1_NW - 1) / K1_NW;
+        const int nmine = (nparts - warp + C::NW - 1) / C::NW;
         const uint64_t* base = p.partial;
         t = m.template merge_batched<8>(
             [&](int i) -> uint64_t {
-              const int pos = i / nmine, part = warp + (i % nmine) * K1_NW;
+              const int pos = i / nmine, part = warp + (i % nmine) * C::NW;
               return __ldcg(reinterpret_cast<const unsigned long long*>(base) + (size_t(part) * NQ + qi) * k + pos);
             },
             nmine * k, t, k, lane);
@@ -387,7 +405,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) scan_stream_kernel(const __grid
         f.clear();
         uint64_t tf = 0ull;
         tf = f.template merge_batched<4>(
-            [&](int i) -> uint64_t { return wk[(i % K1_NW) * C::KSLOTS + i / K1_NW]; }, K1_NW * k, tf, k, lane);
+            [&](int i) -> uint64_t { return wk[(i % C::NW) * C::KSLOTS + i / C::NW]; }, C::NW * k, tf, k, lane);
 #pragma unroll
         for (int j = 0; j < KPL; ++j) {
           const int pos = j * 32 + lane;
@@ -418,10 +436,19 @@ __global__ void __launch_bounds__(K1_THREADS, 1) scan_stream_kernel(const __grid
     }
   } else {
     // ------------------------------ varlen mode ------------------------------
-    // item i -> global warp (i mod total_warps); each item is one row range scanned for up to NQ queries that share
-    // it (the queries of one tenant in this batch, grouped by the host planner: the rows are read once for the group);
-    // the partial lists of every item are merged per query by merge_items_kernel.
-    for (int it = gwarp; it < p.n_items; it += twarps) {
+    // An item is one piece of one row range scanned for up to NQ queries that share it (the queries of one tenant in this
+    // batch, grouped by the host planner: the rows are read once for the group).  The eight warps of the CTA interleave the
+    // item's chunks exactly as in uniform mode, so the CTA streams ONE contiguous window of HBM (per-warp items made every
+    // warp stream its own distant region).  Items are claimed DYNAMICALLY: the host sorts them by size, largest first, CTA c
+    // starts with item c and then takes the next unclaimed one (atomic counter, claimed one item ahead so the latency hides
+    // under the scan) -- longest-processing-time-first, so the launch ends on the smallest pieces instead of on whichever CTA
+    // a static round-robin happened to overload.  Each item's lists are merged in shared memory and written to its own slot
+    // (`ScanItem::out`) of `partial`; merge_items_kernel reduces them per query.
+    uint64_t* wk = reinterpret_cast<uint64_t*>(smem);  // [NW][NQ][KSLOTS], aliases the (idle) ring between items
+    __shared__ int s_claim[2];
+    int it = blockIdx.x;
+    for (int round = 0; it < p.n_items; ++round) {
+      if (threadIdx.x == 0) s_claim[round & 1] = int(gridDim.x + atomicAdd(p.ticket, 1u));
       const ScanItem item = p.items[it];
       nq_live = min(item.nq, NQ);
 #pragma unroll
@@ -446,10 +473,33 @@ __global__ void __launch_bounds__(K1_THREADS, 1) scan_stream_kernel(const __grid
         list[qi].clear();
         thr[qi] = 0ull;
       }
-      scan_range(item.row_begin, item.row_end, 0, 1);
+      scan_range(item.row_begin, item.row_end, warp, C::NW);
+      __syncthreads();   // every warp has consumed the copies it issued: the ring is free to hold the lists
 #pragma unroll
-      for (int qi = 0; qi < NQ; ++qi)
-        if (qi < nq_live) list[qi].store(p.partial + (size_t(it) * p.item_nq + qi) * k, k, lane);
+      for (int qi = 0; qi < NQ; ++qi) {
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) wk[(warp * NQ + qi) * C::KSLOTS + j * 32 + lane] = list[qi].key[j];
+      }
+      __syncthreads();
+      if (warp < nq_live) {
+        const int qi = warp;
+        WarpTopK<KPL> m;
+        m.clear();
+        uint64_t t = 0ull;
+        t = m.template merge_batched<4>(
+            [&](int i) -> uint64_t { return wk[((i % C::NW) * NQ + qi) * C::KSLOTS + i / C::NW]; }, C::NW * k, t, k, lane);
+        m.store(p.partial + (size_t(item.out) * p.item_nq + qi) * k, k, lane);
+      }
+      __syncthreads();   // the lists have been read: the next item's copies may overwrite them
+      it = s_claim[round & 1];   // written before this item's barriers; rewritten two rounds (>= one barrier) from now
+    }
+    // every CTA has made its last claim before it arrives here: the last one to arrive re-arms both counters
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(p.ticket + 1, 1u) == gridDim.x - 1) {
+        p.ticket[0] = 0u;
+        p.ticket[1] = 0u;
+      }
     }
   }
 }

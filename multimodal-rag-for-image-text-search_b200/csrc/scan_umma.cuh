@@ -60,6 +60,12 @@ struct UmmaParams {
   uint32_t* progress;
   int32_t window;
   int32_t skip_epi;   // measurement only: epilogue hands accumulators back without reading them
+  // Fused probe (single-CTA kernel): the first `fused_probe_tiles` tiles of every CTA are scanned twice -- once keeping only
+  // each query's best score, then, after a grid-wide barrier on `grid_barrier` (zeroed by prep_queries_kernel) and the k-th
+  // largest of the per-CTA bests as a proven floor, for real.  Replaces the separate probe and floor launches.
+  int32_t fused_probe_tiles;
+  float* probe_scratch;     // [n_qtiles * n_rslots][128]
+  uint32_t* grid_barrier;
 };
 
 #ifdef __CUDACC__
@@ -188,6 +194,11 @@ __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&v)[
       : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint64_t globaltimer_ns_k2() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // TS = true : the query tile is the A operand *in tensor memory* (128 lanes x D/2 packed-bf16 columns, written once
 //             by the epilogue threads with tcgen05.st); shared memory holds only the index ring (up to 13 x 16 KB
@@ -227,6 +238,10 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   const int ntiles_all = int((nrows + K2_NT - 1) / K2_NT);
   // probe pass: only the first probe_tiles tiles of this CTA's strided sequence
   const int ntiles = p.probe_out ? min(ntiles_all, rs + p.probe_tiles * p.n_rslots) : ntiles_all;
+  // this CTA's tile sequence: [fused probe tiles (scanned for maxima only)] + [all of its tiles]
+  const int n_own = ntiles > rs ? (ntiles - rs + p.n_rslots - 1) / p.n_rslots : 0;
+  const int n_fprobe = min(p.fused_probe_tiles, n_own);
+  const int n_virt = n_own + n_fprobe;
 
   if (threadIdx.x == 0) {
     if ((q_s & 1023u) != 0) __trap();  // SWIZZLE_128B operands need 1024-byte alignment
@@ -263,7 +278,8 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     }
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = rs; t < ntiles; t += p.n_rslots) {
+    for (int v = 0; v < n_virt; ++v) {
+      const int t = rs + (v < n_fprobe ? v : v - n_fprobe) * p.n_rslots;
       const int32_t row0 = int32_t(p.row_begin + uint32_t(t) * K2_NT);
       for (int s = 0; s < ks; ++s) {
         mbar_wait(bar_empty + stage * 8, phase ^ 1u);
@@ -288,7 +304,7 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     tc_fence_after();
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
-    for (int t = rs; t < ntiles; t += p.n_rslots) {
+    for (int v = 0; v < n_virt; ++v) {
       mbar_wait(bar_tempty + acc * 8, acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc_col0 + uint32_t(acc) * K2_NT;
@@ -374,7 +390,48 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     float best = -INFINITY;  // probe pass
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = rs; t < ntiles; t += p.n_rslots) {
+    for (int vt = 0; vt < n_virt; ++vt) {
+      if (vt == n_fprobe && p.fused_probe_tiles > 0) {
+        // ---- end of the fused probe: publish this CTA's per-query maxima, meet every other CTA, derive the floor ----
+        // (a CTA with no tiles of its own still arrives; the producer / MMA warps do not wait here: they run ahead into
+        //  the real tiles until the accumulators are full)
+        p.probe_scratch[size_t(qt * p.n_rslots + rs) * K2_BM + ql] = best;
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (ql == 0) {
+          atomicAdd(p.grid_barrier, 1u);
+          const uint64_t t0 = globaltimer_ns_k2();
+          while (*reinterpret_cast<volatile uint32_t*>(p.grid_barrier) < gridDim.x) {
+            if (globaltimer_ns_k2() - t0 > 20000000ull) break;   // 20 ms: never hang (two such grids on two streams could starve each
+                                                                // other of SMs); without the floor the scan is only slower
+            __nanosleep(64);
+          }
+          __threadfence();
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const bool complete = *reinterpret_cast<volatile uint32_t*>(p.grid_barrier) >= gridDim.x;
+        if (live && complete && p.n_rslots >= k) {
+          // A cheap proven floor: split the CTA slots into k groups (slot mod k) and take each group's best score -- k scores
+          // of k DISTINCT rows -- so their minimum is a lower bound of the final k-th best score.  (Slightly weaker than the
+          // exact k-th largest the separate floor kernel computes, but it is 2 flops per value, branch-free, and every CTA
+          // has to derive it redundantly.)
+          float fl = INFINITY;
+          for (int g = 0; g < k; ++g) {
+            float mg = -INFINITY;
+            for (int r2 = g; r2 < p.n_rslots; r2 += k)
+              mg = fmaxf(mg, __ldcg(p.probe_scratch + size_t(qt * p.n_rslots + r2) * K2_BM + ql));
+            fl = fminf(fl, mg);
+          }
+          if (fl > -INFINITY && fl < INFINITY) {
+            const uint32_t o = f32_orderable(fl);
+            thr_floor = f32_from_orderable(o - (o == 0x80000000u ? 2u : 1u));
+            thr_f = thr_floor;
+          }
+        }
+        thr_key = 0ull;
+      }
+      const bool probing = p.probe_out != nullptr || vt < n_fprobe;
+      const int t = rs + (vt < n_fprobe ? vt : vt - n_fprobe) * p.n_rslots;
       const uint32_t row0 = p.row_begin + uint32_t(t) * K2_NT;
       const int nvalid = int(min(uint32_t(K2_NT), p.row_end - row0));
       mbar_wait(bar_tfull + acc * 8, acc_phase);
@@ -409,7 +466,7 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
               gm[g] = x;
             }
             const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
-            if (p.probe_out != nullptr) {
+            if (probing) {
               best = fmaxf(best, m);
             } else if (m > thr_f) {
 #pragma unroll
@@ -507,8 +564,9 @@ __global__ void probe_floor_kernel(const float* __restrict__ probe, int n_qtiles
 // fp32 queries -> L2-normalised bf16 (LanceDBStore._normalize, then narrowed for the tensor cores). Warp per query.
 template <typename E>
 __global__ void prep_queries_kernel(const float* __restrict__ q, E* __restrict__ out, int B, int dim,
-                                    float* __restrict__ qerr = nullptr) {
+                                    float* __restrict__ qerr = nullptr, uint32_t* __restrict__ zero_word = nullptr) {
   pdl_chain_prologue();
+  if (zero_word != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zero_word = 0u;   // the scan's grid barrier
   const int lane = threadIdx.x & 31;
   const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (qi >= B) return;
@@ -597,7 +655,11 @@ inline size_t umma_workspace_bytes(int sm_count, int dim, int B, int k) {
          umma_align(size_t(ctas) * K2_BM * 4) + umma_align(size_t(B) * 4) + K2_PROGRESS_BYTES + 256;
 }
 
-inline int umma_launches_per_search() { return 5; }  // prep, probe, floor, scan, merge
+inline int& umma_last_launches() {  // kernels launched by the last umma_search on this thread
+  static thread_local int n = 0;
+  return n;
+}
+inline int umma_launches_per_search() { return umma_last_launches(); }
 
 // smem plan: query tile + ring + lists + barriers
 inline int umma_plan_stages(int dim, int k, size_t* smem_bytes, bool ts = false) {

@@ -447,8 +447,10 @@ inline int umma_search(UmmaIndexState& st, Umma2IndexState& st2, const void* row
   float* floor = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(probe) + umma_align(size_t(ctas_max) * K2_BM * 4));
   uint32_t* progress = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(floor) + umma_align(size_t(B) * 4));
   const bool noprobe = options().umma_noprobe != 0;
-  if (dtype == MMR_BF16) launch_pdl(prep_queries_kernel<__nv_bfloat16>, dim3((B + 3) / 4), dim3(128), 0, stream, queries, qb, B, dim, qerr);
-  else launch_pdl(prep_queries_kernel<__half>, dim3((B + 3) / 4), dim3(128), 0, stream, queries, reinterpret_cast<__half*>(qb), B, dim, qerr);
+  uint32_t* grid_barrier = progress + K2_PROGRESS_BYTES / 4 - 16;   // last words of the counter block
+  if (dtype == MMR_BF16) launch_pdl(prep_queries_kernel<__nv_bfloat16>, dim3((B + 3) / 4), dim3(128), 0, stream, queries, qb, B, dim, qerr, grid_barrier);
+  else launch_pdl(prep_queries_kernel<__half>, dim3((B + 3) / 4), dim3(128), 0, stream, queries, reinterpret_cast<__half*>(qb), B, dim, qerr, grid_barrier);
+  int launches = 1;
   const int max_q_per_pass = sm_count * K2_BM;
   for (int q0 = 0; q0 < B; q0 += max_q_per_pass) {
     const int bq = std::min(B - q0, max_q_per_pass);
@@ -493,7 +495,17 @@ inline int umma_search(UmmaIndexState& st, Umma2IndexState& st2, const void* row
     const int grid = pair ? 2 * n_qpairs * p.n_rslots : p.n_qtiles * p.n_rslots;
     // probe pass: worth it when every CTA streams many tiles (the warm-up it removes is ~k ln(n/k) inserts/thread)
     const int64_t tiles_per_cta = ntiles / p.n_rslots;
-    if (!dump && !noprobe && tiles_per_cta >= 8 && p.n_rslots >= k) {
+    // Single-CTA kernel: the probe runs INSIDE the scan launch (first tiles scanned for maxima, grid barrier, floor) --
+    // two launches less on the latency-sensitive small-batch path.  MMR_UMMA_FUSED_PROBE=0 restores the separate pass.
+    const bool want_probe = !dump && !noprobe && tiles_per_cta >= 8 && p.n_rslots >= k;
+    const bool fused_probe = want_probe && !pair && options().umma_fused_probe && grid <= sm_count && q0 == 0 && bq == B;
+    if (fused_probe) {
+      p.fused_probe_tiles = int(std::max<int64_t>(1, std::min<int64_t>(16, tiles_per_cta / 24)));
+      p.probe_scratch = probe;
+      p.grid_barrier = grid_barrier;
+    }
+    if (want_probe && !fused_probe) {
+      launches += 2;
       UmmaParams pp = p;
       pp.probe_out = probe;
       pp.probe_tiles = int(std::max<int64_t>(1, std::min<int64_t>(16, tiles_per_cta / 24)));
@@ -512,6 +524,7 @@ inline int umma_search(UmmaIndexState& st, Umma2IndexState& st2, const void* row
       p.progress = progress;
       p.window = 24;   // tiles: 24 x 128 KB x row slots stays far inside the 126 MB L2
     }
+    launches += dump ? 1 : 2;
     if (dump) {
       if (pair) launch_pdl(scan_umma2_kernel<true>, dim3(grid), dim3(K2_THREADS), smem2_bytes, stream, st2.map, p);
       else if (ts) launch_pdl(scan_umma_kernel<true, true>, dim3(grid), dim3(K2_THREADS), smem_bytes, stream, tm_q, st.map, p);
@@ -529,6 +542,7 @@ inline int umma_search(UmmaIndexState& st, Umma2IndexState& st2, const void* row
                    p.n_rslots, bq, k, out_s + size_t(q0) * k, out_r + size_t(q0) * k, row_base);
     }
   }
+  umma_last_launches() = launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     err = std::string("K2 launch failed: ") + cudaGetErrorString(e);
