@@ -82,6 +82,18 @@ def measured_peaks():
     return 6650.0, 1590.0, "fallback"
 
 
+def sustained_tensor_peak():
+    """cuBLAS bf16 back to back for seconds (power-capped clocks): the denominator for a tensor-bound kernel timed inside a
+    long loop (the burst figure is what one isolated launch can reach).  None when the driver file is absent."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            v = json.load(fh).get("bf16_tflops_sustained")
+        return float(v) if v else None
+    except Exception:
+        return None
+
+
 def load_traffic():
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
@@ -458,6 +470,7 @@ def run_b200(args):
     n_launch = (B + per_pass - 1) // per_pass if lib.mmr_last_kernel() == 1 else 1  # K2: the scan kernel dominates its 5 launches
     kernel_ms = ev2.elapsed_time(ev3) / (K * n_launch)
     hbm_peak, tf_peak, peak_kind = measured_peaks()
+    tf_sustained = sustained_tensor_peak()
     algo_bytes = (hi - lo) * D * esize
 
     def roof(b, ms_per_pass, n_launches=1):
@@ -471,6 +484,8 @@ def run_b200(args):
                "frac": (tfl / tf_peak) if tensor_bound else (gbs / hbm_peak), "traffic": None,
                "peak_kind": f"of {peak_kind}" + (" (cuBLAS bf16 burst)" if tensor_bound else " (copy)"),
                "hbm_GBs": gbs, "tensor_tflops": tfl, "frac_of_nominal_8TBs": gbs / 8000.0,
+               **({"frac_of_sustained_tensor_peak": tfl / tf_sustained, "sustained_tensor_peak": tf_sustained}
+                  if tensor_bound and tf_sustained else {}),
                "algorithmic_bytes_per_launch": algo_bytes, "algorithmic_flops_per_launch": 2.0 * b * (hi - lo) * D / n_launches}
         return out
 

@@ -1,0 +1,17 @@
+#!/bin/bash
+set -u
+O=gpurun_out/r2r
+mkdir -p $O
+timeout 900 python -m pytest tests/test_gpu_encoders.py -m gpu -q -x > $O/pytest_enc.log 2>&1; echo "pytest rc=$?" >> $O/pytest_enc.log
+MMR_ENC_FUSE_LN=0 timeout 900 python -m pytest tests/test_gpu_encoders.py -m gpu -q -x > $O/pytest_enc_nofuse.log 2>&1; echo "pytest rc=$?" >> $O/pytest_enc_nofuse.log
+python benchmarks/encoder_bench.py > $O/encoder_bench.json 2> $O/encoder_bench.err
+MMR_ENC_FUSE_LN=0 python benchmarks/encoder_bench.py > $O/encoder_bench_nofuse.json 2>> $O/encoder_bench.err
+tail -3 $O/pytest_enc.log; tail -2 $O/pytest_enc_nofuse.log
+python - <<'P'
+import json
+for f in ("encoder_bench.json","encoder_bench_nofuse.json"):
+    try:
+        d=json.load(open("gpurun_out/r2r/"+f)); print(f, [(r["model"], r["batch"], r["seq"], round(r["device_encoder_ms"],3), r["kernel_launches"]) for r in d["results"]])
+    except Exception as e: print(f,"ERR",e)
+P
+tail -3 $O/encoder_bench.err

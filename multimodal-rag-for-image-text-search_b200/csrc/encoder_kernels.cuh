@@ -39,6 +39,13 @@ struct GemmParams {
   const float* residual;      // [M, N] fp32 (EPI_BIAS_RES_F32)
   float* out_f32;             // [M, N]
   __nv_bfloat16* out_bf16;    // [M, N]
+  // LNX variant: the token operand is LN(ln_src) computed in the kernel (ln_src fp32 [M, K]); CTAs of feature tile 0 also
+  // write the normalised rows to ln_out (fp32 [M, K], may be null, may NOT alias ln_src)
+  const float* ln_src;
+  const float* ln_g;
+  const float* ln_b;
+  float* ln_out;
+  float ln_eps;
 };
 
 #ifdef __CUDACC__
@@ -56,7 +63,13 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
 
 // out[t, f] = epilogue( sum_k X[t, k] * W[f, k] + bias[f] )      grid = (N / 128, ceil(M / NT))
-template <int EPI, int NT>
+// LNX = true: X = LayerNorm(ln_src) is computed HERE instead of by a layernorm_kernel launch in front (one dependent launch
+// less per LayerNorm: at query sizes a forward pass is a chain of ~5 us launches, profiles/r02_encoder_summary.md).  The four
+// epilogue warps (idle until the accumulator is ready) normalise the tile's tokens -- warp per token, fp32, two-pass like
+// warp_layernorm -- and write the bf16 operand straight into shared memory in the layout TMA's SWIZZLE_128B would have
+// produced (16-byte chunk c of row r at chunk c ^ (r & 7)); all K / 64 slices stay resident (K <= 512, NT = 64: <= 64 KB),
+// the ring carries only weight tiles, and those start loading under the previous kernel (weights are not chain outputs).
+template <int EPI, int NT, bool LNX = false>
 __global__ void __launch_bounds__(ENC_THREADS, 1)
 gemm_wt_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x, const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -69,12 +82,14 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
   constexpr int ENC_NT = NT;
   constexpr int ENC_X_SLICE = NT * 128;                             // [NT tokens x 64 bf16]
   const uint32_t w_s = smem_u32(smem);                              // [nst][16 KB]
-  const uint32_t x_s = w_s + uint32_t(nst) * ENC_W_SLICE;           // [nst][NT * 128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(nst) * (ENC_W_SLICE + ENC_X_SLICE));
+  const uint32_t x_s = w_s + uint32_t(nst) * ENC_W_SLICE;           // [nst][NT * 128 B]   (LNX: [K / 64][NT * 128 B])
+  const int nx = LNX ? ks : nst;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(nst) * ENC_W_SLICE + size_t(nx) * ENC_X_SLICE);
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = bar_full + ENC_MAX_STAGES * 8;
   const uint32_t bar_acc = bar_empty + ENC_MAX_STAGES * 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ENC_MAX_STAGES + 1);
+  const uint32_t bar_x = bar_acc + 8;                               // LNX: the normalised token operand is in shared memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ENC_MAX_STAGES + 2);
   const int f0 = blockIdx.x * ENC_BM;
   const int t0 = blockIdx.y * ENC_NT;
 
@@ -85,9 +100,10 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       mbar_init(bar_empty + s * 8, 1);
     }
     mbar_init(bar_acc, 1);
+    mbar_init(bar_x, 128);
     fence_mbar_init();
     tma_prefetch_desc(&tm_w);
-    tma_prefetch_desc(&tm_x);
+    if constexpr (!LNX) tma_prefetch_desc(&tm_x);
   }
   if (warp == 1) tmem_alloc_cols(smem_u32(tmem_slot), ENC_NT);
   tc_fence_before();
@@ -99,13 +115,14 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
     const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
-    pdl_wait_prior_grid();   // the activation tile is the previous kernel's output
+    if constexpr (!LNX) pdl_wait_prior_grid();   // the activation tile is the previous kernel's output
     for (int s = 0; s < ks; ++s) {
       mbar_wait(bar_empty + stage * 8, phase ^ 1u);
       if (leader) {
-        mbar_arrive_expect_tx(bar_full + stage * 8, ENC_W_SLICE + ENC_X_SLICE);
+        mbar_arrive_expect_tx(bar_full + stage * 8, LNX ? ENC_W_SLICE : ENC_W_SLICE + ENC_X_SLICE);
         tma_load_2d(w_s + stage * ENC_W_SLICE, &tm_w, bar_full + stage * 8, s * 64, f0);
-        tma_load_2d(x_s + stage * ENC_X_SLICE, &tm_x, bar_full + stage * 8, s * 64, t0);   // rows past M are zero-filled
+        if constexpr (!LNX)
+          tma_load_2d(x_s + stage * ENC_X_SLICE, &tm_x, bar_full + stage * 8, s * 64, t0);   // rows past M are zero-filled
       }
       __syncwarp();
       if (++stage == nst) {
@@ -118,11 +135,12 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
     const uint32_t idesc = enc_idesc(NT);
     int stage = 0;
     uint32_t phase = 0;
+    if constexpr (LNX) mbar_wait(bar_x, 0);
     for (int s = 0; s < ks; ++s) {
       mbar_wait(bar_full + stage * 8, phase);
       tc_fence_after();
       const uint64_t a_desc = umma_smem_desc(w_s + stage * ENC_W_SLICE);
-      const uint64_t b_desc = umma_smem_desc(x_s + stage * ENC_X_SLICE);
+      const uint64_t b_desc = umma_smem_desc(x_s + (LNX ? s : stage) * ENC_X_SLICE);
       if (leader) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
@@ -142,7 +160,74 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
     const int quarter = warp & 3;
     const int f = f0 + quarter * 32 + lane;
     const float b = p.bias ? p.bias[f] : 0.f;
-    pdl_wait_prior_grid();   // residual / output buffers belong to the chain
+    float4 ln_g4[4], ln_b4[4];
+    if constexpr (LNX) {   // LayerNorm weights are not chain outputs: fetched under the previous kernel
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < (p.K >> 7)) {
+          ln_g4[j] = *reinterpret_cast<const float4*>(p.ln_g + j * 128 + lane * 4);
+          ln_b4[j] = *reinterpret_cast<const float4*>(p.ln_b + j * 128 + lane * 4);
+        }
+    }
+    pdl_wait_prior_grid();   // ln_src / residual / output buffers belong to the chain
+    if constexpr (LNX) {
+      // lane l holds columns [j * 128 + 4 l, +4) of a token, j < K / 128: float4 loads, 8-byte bf16x4 stores.  Four tokens per
+      // warp per round with all their loads in flight together (one L2 latency per round, not per token).  Token rows past M
+      // are left as they are: an accumulator column depends on its own token row only, and those columns are never stored.
+      const int nv = p.K >> 7;
+      const int nlive = min(NT, p.M - t0);
+      const bool writer = blockIdx.x == 0 && p.ln_out != nullptr;
+      for (int tb = warp - 2; tb < nlive; tb += 16) {
+        float4 x[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            x[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < nv && tb + 4 * u < nlive)
+              x[u][j] = __ldcg(reinterpret_cast<const float4*>(p.ln_src + size_t(t0 + tb + 4 * u) * p.K + j * 128) + lane);
+          }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int tt = tb + 4 * u;
+          if (tt >= nlive) break;   // warp-uniform
+          float sum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sum += (x[u][j].x + x[u][j].y) + (x[u][j].z + x[u][j].w);
+          const float mean = warp_allreduce_sum(sum) / float(p.K);
+          float var = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < nv) {
+              const float d0 = x[u][j].x - mean, d1 = x[u][j].y - mean, d2 = x[u][j].z - mean, d3 = x[u][j].w - mean;
+              var = fmaf(d0, d0, var);
+              var = fmaf(d1, d1, var);
+              var = fmaf(d2, d2, var);
+              var = fmaf(d3, d3, var);
+            }
+          const float rstd = rsqrtf(warp_allreduce_sum(var) / float(p.K) + p.ln_eps);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < nv) {
+              const int col = j * 128 + lane * 4;
+              float4 y;
+              y.x = (x[u][j].x - mean) * rstd * ln_g4[j].x + ln_b4[j].x;
+              y.y = (x[u][j].y - mean) * rstd * ln_g4[j].y + ln_b4[j].y;
+              y.z = (x[u][j].z - mean) * rstd * ln_g4[j].z + ln_b4[j].z;
+              y.w = (x[u][j].w - mean) * rstd * ln_g4[j].w + ln_b4[j].w;
+              if (writer) *reinterpret_cast<float4*>(p.ln_out + size_t(t0 + tt) * p.K + col) = y;
+              const __nv_bfloat162 lo = __floats2bfloat162_rn(y.x, y.y), hi = __floats2bfloat162_rn(y.z, y.w);
+              const int slice = col >> 6, cc = col & 63;
+              const uint32_t dst = x_s + uint32_t(slice) * ENC_X_SLICE + uint32_t(tt) * 128u +
+                                   (uint32_t((cc >> 3) ^ (tt & 7)) << 4) + uint32_t(cc & 7) * 2u;
+              asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(*reinterpret_cast<const uint32_t*>(&lo)),
+                           "r"(*reinterpret_cast<const uint32_t*>(&hi)) : "memory");
+            }
+        }
+      }
+      fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      mbar_arrive(bar_x);
+    }
     mbar_wait(bar_acc, 0);
     tc_fence_after();
 #pragma unroll 1

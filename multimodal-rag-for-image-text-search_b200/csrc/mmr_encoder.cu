@@ -235,7 +235,7 @@ static int launch_gemm_nt(const CUtensorMap& mw, const CUtensorMap& mx, int M, i
   p.residual = residual;
   p.out_f32 = out_f32;
   p.out_bf16 = out_bf16;
-  const size_t smem = size_t(p.nstages) * stage_bytes + (2 * ENC_MAX_STAGES + 2) * 8 + 64;
+  const size_t smem = size_t(p.nstages) * stage_bytes + (2 * ENC_MAX_STAGES + 3) * 8 + 64;
   if (!attr_done[dev & 63]) {
     CUDA_TRY(cudaFuncSetAttribute(gemm_wt_kernel<EPI, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     attr_done[dev & 63] = true;
@@ -253,6 +253,38 @@ static int launch_gemm(const CUtensorMap& mw, const CUtensorMap& mx, int M, int 
     case 128: return launch_gemm_nt<EPI, 128>(mw, mx, M, N, K, bias, residual, out_f32, out_bf16, st);
     default: return launch_gemm_nt<EPI, 256>(mw, mx, M, N, K, bias, residual, out_f32, out_bf16, st);
   }
+}
+
+// The same GEMM with the LayerNorm in front of it folded in (gemm_wt_kernel<EPI, 64, true>): X = LN(ln_src), normalised rows
+// also written to ln_out (fp32) when the residual stream needs them.  Token tile 64 only (the latency-bound regime).
+template <int EPI>
+static int launch_gemm_ln(const CUtensorMap& mw, const CUtensorMap& any_x_map, int M, int N, int K, const float* bias,
+                          float* out_f32, __nv_bfloat16* out_bf16, const float* ln_src, const float* ln_g, const float* ln_b,
+                          float ln_eps, float* ln_out, cudaStream_t st) {
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  GemmParams p{};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.nstages = std::min(ENC_MAX_STAGES, K / 64);
+  p.bias = bias;
+  p.out_f32 = out_f32;
+  p.out_bf16 = out_bf16;
+  p.ln_src = ln_src;
+  p.ln_g = ln_g;
+  p.ln_b = ln_b;
+  p.ln_out = ln_out;
+  p.ln_eps = ln_eps;
+  const size_t smem = size_t(p.nstages) * ENC_W_SLICE + size_t(K / 64) * (64 * 128) + (2 * ENC_MAX_STAGES + 3) * 8 + 64;
+  if (!attr_done[dev & 63]) {
+    CUDA_TRY(cudaFuncSetAttribute(gemm_wt_kernel<EPI, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    attr_done[dev & 63] = true;
+  }
+  CUDA_TRY(launch_pdl(gemm_wt_kernel<EPI, 64, true>, dim3(N / ENC_BM, (M + 63) / 64), dim3(ENC_THREADS), smem, st, mw, any_x_map, p));
+  mmr_g_launches++;
+  return MMR_OK;
 }
 
 template <int H>
@@ -289,14 +321,32 @@ static int forward_t(mmr_encoder* e, int B, int S, float* out_dev, cudaStream_t 
     CUDA_TRY(launch_pdl(embed_kernel<H>, rows_grid, rows_block, 0, st, e->d_ids, e->d_types, e->word, e->pos, e->type_emb,
                         e->emb_ln_w, e->emb_ln_b, c.ln_eps, M, S, e->x, e->x16));
   mmr_g_launches++;
+  // LayerNorms in front of a GEMM are folded into it for a single short query (<= 16 tokens: one round of four tokens per
+  // epilogue warp).  Measured (profiles/r02_encoder_summary.md): 44 -> 33 / 86 -> 62 launches, MiniLM 1 x 16 unchanged, CLIP 1 x 16
+  // -5 %; from 128 tokens on the redundant per-CTA LayerNorm is slower than one layernorm_kernel launch (a dependent launch
+  // costs no more than the work it replaces), so larger passes keep the separate kernel.  MMR_ENC_FUSE_LN=0: never fold;
+  // =2: fold whenever the token tile is 64 (measurement).
+  const int fuse_opt = options().enc_fuse_ln;
+  const bool fuse_ln = fuse_opt == 2 ? enc_token_tile(M) == 64 : (fuse_opt == 1 && M <= 16);
+  const LayerW* prev = nullptr;   // BERT: the layer whose closing LayerNorm (ln2 over e->tmp) is still pending
   for (LayerW& L : e->layers) {
     int rc;
     if (clip) {  // pre-LN: h = LN1(x)
-      CUDA_TRY(launch_pdl(layernorm_kernel<H>, rows_grid, rows_block, 0, st, e->x, L.ln1_w, L.ln1_b, c.ln_eps, M,
-                          (float*)nullptr, e->x16));
-      mmr_g_launches++;
+      if (fuse_ln) {
+        rc = launch_gemm_ln<EPI_BIAS_F32>(L.m_qkv, e->m_x16, M, 3 * H, H, L.qkv_b, e->qkv, nullptr, e->x, L.ln1_w, L.ln1_b, c.ln_eps,
+                                          nullptr, st);
+      } else {
+        CUDA_TRY(launch_pdl(layernorm_kernel<H>, rows_grid, rows_block, 0, st, e->x, L.ln1_w, L.ln1_b, c.ln_eps, M,
+                            (float*)nullptr, e->x16));
+        mmr_g_launches++;
+        rc = launch_gemm<EPI_BIAS_F32>(L.m_qkv, e->m_x16, M, 3 * H, H, L.qkv_b, nullptr, e->qkv, nullptr, st);
+      }
+    } else if (prev != nullptr) {   // BERT, fused: x = LN2_prev(tmp) computed by this layer's QKV GEMM
+      rc = launch_gemm_ln<EPI_BIAS_F32>(L.m_qkv, e->m_x16, M, 3 * H, H, L.qkv_b, e->qkv, nullptr, e->tmp, prev->ln2_w, prev->ln2_b,
+                                        c.ln_eps, e->x, st);
+    } else {
+      rc = launch_gemm<EPI_BIAS_F32>(L.m_qkv, e->m_x16, M, 3 * H, H, L.qkv_b, nullptr, e->qkv, nullptr, st);
     }
-    rc = launch_gemm<EPI_BIAS_F32>(L.m_qkv, e->m_x16, M, 3 * H, H, L.qkv_b, nullptr, e->qkv, nullptr, st);
     if (rc != MMR_OK) return rc;
     if (DH == 32)
       CUDA_TRY(launch_pdl(attention_kernel<32>, dim3(c.heads, B), dim3(ATT_NW * 32), att_smem, st, e->qkv, e->d_mask, e->ctx16, S, H,
@@ -309,10 +359,15 @@ static int forward_t(mmr_encoder* e, int B, int S, float* out_dev, cudaStream_t 
       // x = x + out_proj(ctx); h = LN2(x); x = x + fc2(quick_gelu(fc1(h)))
       rc = launch_gemm<EPI_BIAS_RES_F32>(L.m_o, e->m_ctx16, M, H, H, L.o_b, e->x, e->x, nullptr, st);
       if (rc != MMR_OK) return rc;
-      CUDA_TRY(launch_pdl(layernorm_kernel<H>, rows_grid, rows_block, 0, st, e->x, L.ln2_w, L.ln2_b, c.ln_eps, M,
-                          (float*)nullptr, e->x16));
-      mmr_g_launches++;
-      rc = launch_gemm<EPI_QUICKGELU_BF16>(L.m_fc1, e->m_x16, M, I, H, L.fc1_b, nullptr, nullptr, e->h16, st);
+      if (fuse_ln) {
+        rc = launch_gemm_ln<EPI_QUICKGELU_BF16>(L.m_fc1, e->m_x16, M, I, H, L.fc1_b, nullptr, e->h16, e->x, L.ln2_w, L.ln2_b, c.ln_eps,
+                                                nullptr, st);
+      } else {
+        CUDA_TRY(launch_pdl(layernorm_kernel<H>, rows_grid, rows_block, 0, st, e->x, L.ln2_w, L.ln2_b, c.ln_eps, M,
+                            (float*)nullptr, e->x16));
+        mmr_g_launches++;
+        rc = launch_gemm<EPI_QUICKGELU_BF16>(L.m_fc1, e->m_x16, M, I, H, L.fc1_b, nullptr, nullptr, e->h16, st);
+      }
       if (rc != MMR_OK) return rc;
       rc = launch_gemm<EPI_BIAS_RES_F32>(L.m_fc2, e->m_h16, M, H, I, L.fc2_b, e->x, e->x, nullptr, st);
       if (rc != MMR_OK) return rc;
@@ -320,14 +375,23 @@ static int forward_t(mmr_encoder* e, int B, int S, float* out_dev, cudaStream_t 
       // post-LN (BERT): x = LN1(x + out_proj(ctx)); x = LN2(x + fc2(gelu(fc1(x))))
       rc = launch_gemm<EPI_BIAS_RES_F32>(L.m_o, e->m_ctx16, M, H, H, L.o_b, e->x, e->tmp, nullptr, st);
       if (rc != MMR_OK) return rc;
-      CUDA_TRY(launch_pdl(layernorm_kernel<H>, rows_grid, rows_block, 0, st, e->tmp, L.ln1_w, L.ln1_b, c.ln_eps, M, e->x, e->x16));
-      mmr_g_launches++;
-      rc = launch_gemm<EPI_GELU_BF16>(L.m_fc1, e->m_x16, M, I, H, L.fc1_b, nullptr, nullptr, e->h16, st);
+      if (fuse_ln) {
+        rc = launch_gemm_ln<EPI_GELU_BF16>(L.m_fc1, e->m_x16, M, I, H, L.fc1_b, nullptr, e->h16, e->tmp, L.ln1_w, L.ln1_b, c.ln_eps,
+                                           e->x, st);
+      } else {
+        CUDA_TRY(launch_pdl(layernorm_kernel<H>, rows_grid, rows_block, 0, st, e->tmp, L.ln1_w, L.ln1_b, c.ln_eps, M, e->x, e->x16));
+        mmr_g_launches++;
+        rc = launch_gemm<EPI_GELU_BF16>(L.m_fc1, e->m_x16, M, I, H, L.fc1_b, nullptr, nullptr, e->h16, st);
+      }
       if (rc != MMR_OK) return rc;
       rc = launch_gemm<EPI_BIAS_RES_F32>(L.m_fc2, e->m_h16, M, H, I, L.fc2_b, e->x, e->tmp, nullptr, st);
       if (rc != MMR_OK) return rc;
-      CUDA_TRY(launch_pdl(layernorm_kernel<H>, rows_grid, rows_block, 0, st, e->tmp, L.ln2_w, L.ln2_b, c.ln_eps, M, e->x, e->x16));
-      mmr_g_launches++;
+      if (fuse_ln && &L != &e->layers.back()) {
+        prev = &L;   // LN2 rides in the next layer's QKV GEMM
+      } else {
+        CUDA_TRY(launch_pdl(layernorm_kernel<H>, rows_grid, rows_block, 0, st, e->tmp, L.ln2_w, L.ln2_b, c.ln_eps, M, e->x, e->x16));
+        mmr_g_launches++;
+      }
     }
   }
   // head

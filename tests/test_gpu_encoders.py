@@ -79,6 +79,34 @@ def test_minilm_text_encoder_matches_fp32_torch(enc_mod, bert, b, s):
     enc.close()
 
 
+def test_layernorm_folded_into_the_gemm_matches_the_separate_kernel(enc_mod, bert):
+    """gemm_wt_kernel<EPI, 64, true> computes the LayerNorm in front of a GEMM itself (shipped for passes of <= 16 tokens,
+    MMR_ENC_FUSE_LN=2 forces it for every pass on the 64-token tile): same embeddings as the layernorm_kernel path, and both
+    inside the fp32-torch tolerance."""
+    native = importlib.import_module(PKG + "._native")
+    enc = enc_mod.DeviceEncoder.from_hf_bert(bert)
+    g = torch.Generator().manual_seed(77)
+    try:
+        for b, s in ((1, 12), (1, 16), (4, 40), (9, 100)):     # 12 / 16 / 160 / 900 tokens: 1, 1, 3 and 15 token tiles
+            ids = torch.randint(1000, 30000, (b, s), generator=g)
+            lens = torch.randint(max(1, s // 2), s + 1, (b,), generator=g)
+            lens[0] = s
+            mask = (torch.arange(s)[None, :] < lens[:, None]).long()
+            want = _bert_reference(bert, ids, mask)
+            outs = {}
+            for mode in ("0", "2"):
+                native.set_option("MMR_ENC_FUSE_LN", mode)
+                n0 = native.lib().mmr_launch_count()
+                outs[mode] = enc.forward_ids(ids.numpy(), mask.numpy()).cpu()
+                outs[mode + "n"] = native.lib().mmr_launch_count() - n0
+                assert (outs[mode] - want).abs().max().item() <= TOL, (mode, b, s)
+            assert outs["2n"] == outs["0n"] - 11, (outs["0n"], outs["2n"])       # 2 per layer, minus the last layer's closing LN
+            assert (outs["0"] - outs["2"]).abs().max().item() <= 2e-4, (b, s)
+    finally:
+        native.set_option("MMR_ENC_FUSE_LN", None)
+        enc.close()
+
+
 def test_clip_text_tower_matches_fp32_torch(enc_mod):
     from transformers import CLIPTextConfig, CLIPTextModelWithProjection
     torch.manual_seed(1)
