@@ -58,8 +58,12 @@ struct Options {
                              //                         profiles/r02_k2_summary.md; kept as a measurement switch)
   int umma_skip_epi = 0;  // MMR_UMMA_SKIP_EPI=1  K2 pair mode skips the accumulator read-back (WRONG results; measures what the
                           //                      MMA pipeline alone reaches: profiles/r02_k2_summary.md)
-  int enc_fuse_ln = 1;    // MMR_ENC_FUSE_LN     device encoders: LayerNorm folded into the GEMM behind it: 1 = for passes of <= 16
-                          //                     tokens (default), 0 = never, 2 = whenever the token tile is 64 (measurement)
+  int enc_fuse_ln = 0;    // MMR_ENC_FUSE_LN     device encoders: LayerNorm folded into the GEMM behind it (gemm_wt_kernel<.., true>):
+                          //                     0 = never (default: measured no faster, profiles/r02_encoder_summary.md), 1 = for
+                          //                     passes of <= 16 tokens, 2 = whenever the token tile is 64
+  int enc_att_mma = 1;    // MMR_ENC_ATT_MMA     device encoders: 1 = the cross-encoder runs attention_mma_kernel (bf16 tensor-core
+                          //                     contractions), the query encoders the fp32 kernel (default); 0 = fp32 everywhere;
+                          //                     2 = every model from 96 tokens on (measurement)
   int inline_query = 1;   // MMR_INLINE_QUERY=0  host-buffer calls always stage the query with an H2D copy (measurement)
   int mailbox = 0;        // MMR_MAILBOX=1       host-buffer calls spin on a flag the kernel writes into the mapped mailbox instead
                           //                     of synchronising the stream (measured no faster: profiles/r02_fixed_cost.json)

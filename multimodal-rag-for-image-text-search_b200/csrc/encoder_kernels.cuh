@@ -65,8 +65,8 @@ __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf
 // out[t, f] = epilogue( sum_k X[t, k] * W[f, k] + bias[f] )      grid = (N / 128, ceil(M / NT))
 // LNX = true: X = LayerNorm(ln_src) is computed HERE instead of by a layernorm_kernel launch in front (one dependent launch
 // less per LayerNorm: at query sizes a forward pass is a chain of ~5 us launches, profiles/r02_encoder_summary.md).  The four
-// epilogue warps (idle until the accumulator is ready) normalise the tile's tokens -- warp per token, fp32, two-pass like
-// warp_layernorm -- and write the bf16 operand straight into shared memory in the layout TMA's SWIZZLE_128B would have
+// epilogue warps (idle until the accumulator is ready) normalise the tile's tokens -- warp per token, bit for bit
+// warp_layernorm's arithmetic -- and write the bf16 operand straight into shared memory in the layout TMA's SWIZZLE_128B would have
 // produced (16-byte chunk c of row r at chunk c ^ (r & 7)); all K / 64 slices stay resident (K <= 512, NT = 64: <= 64 KB),
 // the ring carries only weight tiles, and those start loading under the previous kernel (weights are not chain outputs).
 template <int EPI, int NT, bool LNX = false>
@@ -160,32 +160,33 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
     const int quarter = warp & 3;
     const int f = f0 + quarter * 32 + lane;
     const float b = p.bias ? p.bias[f] : 0.f;
-    float4 ln_g4[4], ln_b4[4];
+    float ln_gr[16], ln_br[16];
     if constexpr (LNX) {   // LayerNorm weights are not chain outputs: fetched under the previous kernel
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (j < (p.K >> 7)) {
-          ln_g4[j] = *reinterpret_cast<const float4*>(p.ln_g + j * 128 + lane * 4);
-          ln_b4[j] = *reinterpret_cast<const float4*>(p.ln_b + j * 128 + lane * 4);
+      for (int i = 0; i < 16; ++i)
+        if (i < (p.K >> 5)) {
+          ln_gr[i] = p.ln_g[i * 32 + lane];
+          ln_br[i] = p.ln_b[i * 32 + lane];
         }
     }
     pdl_wait_prior_grid();   // ln_src / residual / output buffers belong to the chain
     if constexpr (LNX) {
-      // lane l holds columns [j * 128 + 4 l, +4) of a token, j < K / 128: float4 loads, 8-byte bf16x4 stores.  Four tokens per
-      // warp per round with all their loads in flight together (one L2 latency per round, not per token).  Token rows past M
-      // are left as they are: an accumulator column depends on its own token row only, and those columns are never stored.
-      const int nv = p.K >> 7;
+      // Warp per token with EXACTLY layernorm_kernel's arithmetic (lane l holds columns i * 32 + l, sums in the same order):
+      // the folded and the separate path give bit-identical activations, so an embedding does not depend on whether its
+      // pass was short enough to be folded.  Four tokens per warp per round with all their loads in flight together (one L2
+      // latency per round, not per token).  Token rows past M are left as they are: an accumulator column depends on its own
+      // token row only, and those columns are never stored.
+      const int ni = p.K >> 5;
       const int nlive = min(NT, p.M - t0);
       const bool writer = blockIdx.x == 0 && p.ln_out != nullptr;
       for (int tb = warp - 2; tb < nlive; tb += 16) {
-        float4 x[4][4];
+        float x[4][16];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            x[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j < nv && tb + 4 * u < nlive)
-              x[u][j] = __ldcg(reinterpret_cast<const float4*>(p.ln_src + size_t(t0 + tb + 4 * u) * p.K + j * 128) + lane);
+          for (int i = 0; i < 16; ++i) {
+            x[u][i] = 0.f;
+            if (i < ni && tb + 4 * u < nlive) x[u][i] = __ldcg(p.ln_src + size_t(t0 + tb + 4 * u) * p.K + i * 32 + lane);
           }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -193,35 +194,28 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
           if (tt >= nlive) break;   // warp-uniform
           float sum = 0.f;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) sum += (x[u][j].x + x[u][j].y) + (x[u][j].z + x[u][j].w);
+          for (int i = 0; i < 16; ++i)
+            if (i < ni) sum += x[u][i];
           const float mean = warp_allreduce_sum(sum) / float(p.K);
           float var = 0.f;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (j < nv) {
-              const float d0 = x[u][j].x - mean, d1 = x[u][j].y - mean, d2 = x[u][j].z - mean, d3 = x[u][j].w - mean;
-              var = fmaf(d0, d0, var);
-              var = fmaf(d1, d1, var);
-              var = fmaf(d2, d2, var);
-              var = fmaf(d3, d3, var);
+          for (int i = 0; i < 16; ++i)
+            if (i < ni) {
+              const float d = x[u][i] - mean;
+              var = fmaf(d, d, var);
             }
           const float rstd = rsqrtf(warp_allreduce_sum(var) / float(p.K) + p.ln_eps);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (j < nv) {
-              const int col = j * 128 + lane * 4;
-              float4 y;
-              y.x = (x[u][j].x - mean) * rstd * ln_g4[j].x + ln_b4[j].x;
-              y.y = (x[u][j].y - mean) * rstd * ln_g4[j].y + ln_b4[j].y;
-              y.z = (x[u][j].z - mean) * rstd * ln_g4[j].z + ln_b4[j].z;
-              y.w = (x[u][j].w - mean) * rstd * ln_g4[j].w + ln_b4[j].w;
-              if (writer) *reinterpret_cast<float4*>(p.ln_out + size_t(t0 + tt) * p.K + col) = y;
-              const __nv_bfloat162 lo = __floats2bfloat162_rn(y.x, y.y), hi = __floats2bfloat162_rn(y.z, y.w);
-              const int slice = col >> 6, cc = col & 63;
+          for (int i = 0; i < 16; ++i)
+            if (i < ni) {
+              const int c = i * 32 + lane;
+              const float y = (x[u][i] - mean) * rstd * ln_gr[i] + ln_br[i];
+              if (writer) p.ln_out[size_t(t0 + tt) * p.K + c] = y;
+              const int slice = c >> 6, cc = c & 63;
               const uint32_t dst = x_s + uint32_t(slice) * ENC_X_SLICE + uint32_t(tt) * 128u +
                                    (uint32_t((cc >> 3) ^ (tt & 7)) << 4) + uint32_t(cc & 7) * 2u;
-              asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(*reinterpret_cast<const uint32_t*>(&lo)),
-                           "r"(*reinterpret_cast<const uint32_t*>(&hi)) : "memory");
+              const __nv_bfloat16 yb = __float2bfloat16_rn(y);
+              asm volatile("st.shared.b16 [%0], %1;" ::"r"(dst), "h"(*reinterpret_cast<const uint16_t*>(&yb)) : "memory");
             }
         }
       }
@@ -461,6 +455,198 @@ __global__ void __launch_bounds__(ATT_NW * 32) attention_kernel(const float* __r
       }
     }
     __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- attention, long sequences
+// Rerank passages are 128-512 tokens (reference index_build.py:14 splits at 512 tokens): there the fp32 kernel above is
+// shared-memory-bound (five LDS per four FMAs in the P.V loop; 425 us per layer at 8 x 512, 75 % of the pass).  This one
+// runs both contractions on the tensor cores, flash-attention style, with warp-level mma.sync m16n8k16 (bf16 in, fp32
+// accumulate): the natural tile for head dim 32 / 64 -- a tcgen05 tile is 128 rows with the accumulator in tensor memory,
+// and the online softmax between the two contractions would cross TMEM <-> registers twice per key block for a layer whose
+// total work is 3 GFLOP.  grid = (heads, B, ceil(S / 128)); a CTA = 8 warps x 16 query rows; K [S][DH] and V^T [DH][S] of
+// the head live in shared memory as bf16 (row pads make every fragment load conflict-free); scores never leave registers:
+// per 64-key block S = Q K^T (fp32 accumulators), running max / sum, P packed to bf16 straight from the accumulator
+// registers (the m16n8 C layout IS the m16n8k16 A layout), O += P V.  Q is scaled in fp32 before narrowing.
+// Used for the cross-encoder (every sequence length: which kernel runs must not depend on what a pair is batched with; a
+// pair's logit is independent of the padded length -- masked and zero-filled keys contribute exact zeros); the query
+// encoders, whose embeddings are held to 1e-3 of fp32 torch, stay on the fp32 kernel.
+constexpr int ATC_NW = 8;
+constexpr int ATC_ROWS = ATC_NW * 16;   // query rows per CTA
+constexpr int ATC_KB = 64;              // keys per online-softmax block
+constexpr int ATC_MIN_S = 96;           // MMR_ENC_ATT_MMA=2 (measurement): every model from this sequence length on
+
+template <int DH>
+inline size_t attention_mma_smem_bytes(int S) {
+  const int sp = (S + ATC_KB - 1) / ATC_KB * ATC_KB;
+  return size_t(sp) * (DH + 8) * 2 + size_t(DH) * (sp + 8) * 2 + size_t(sp) * 4;
+}
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);   // .x (low half) = lo
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+template <int DH>
+__global__ void __launch_bounds__(ATC_NW * 32) attention_mma_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ mask,
+                                                                   __nv_bfloat16* __restrict__ ctx, int S, int H, int causal) {
+  extern __shared__ __align__(16) uint8_t atc_smem[];
+  pdl_chain_prologue();
+  constexpr int KP = DH + 8;                      // K row pitch (bf16): 80 / 144 bytes -> the 8 rows of a fragment hit 8 bank groups
+  const int sp = (S + ATC_KB - 1) / ATC_KB * ATC_KB;
+  const int VP = sp + 8;                          // V^T row pitch (bf16)
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(atc_smem);                 // [sp][KP]
+  __nv_bfloat16* Vt = Ks + size_t(sp) * KP;                                       // [DH][VP]
+  float* madd = reinterpret_cast<float*>(Vt + size_t(DH) * VP);                   // [sp] 0 or -inf (padding keys, keys >= S)
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const size_t row0 = size_t(b) * S;
+  const int ld = 3 * H;
+  const int q_lo = blockIdx.z * ATC_ROWS;                                         // this CTA's query rows [q_lo, q_lo + 128)
+  const int kend = causal ? min(sp, (min(q_lo + ATC_ROWS, S) + ATC_KB - 1) / ATC_KB * ATC_KB) : sp;   // keys this CTA can need
+
+  // ---- stage K (row-major) and V (transposed) of this head as bf16, and the additive key mask ----
+  for (int i = threadIdx.x; i < kend * (DH / 4); i += blockDim.x) {
+    const int j = i / (DH / 4), d4 = (i % (DH / 4)) * 4;
+    float4 k4 = make_float4(0.f, 0.f, 0.f, 0.f), v4 = k4;
+    if (j < S) {
+      const float* src = qkv + (row0 + j) * ld + h * DH + d4;
+      k4 = *reinterpret_cast<const float4*>(src + H);
+      v4 = *reinterpret_cast<const float4*>(src + 2 * H);
+    }
+    uint2 kk;
+    kk.x = pack_bf16x2(k4.x, k4.y);
+    kk.y = pack_bf16x2(k4.z, k4.w);
+    *reinterpret_cast<uint2*>(Ks + size_t(j) * KP + d4) = kk;
+    Vt[size_t(d4 + 0) * VP + j] = __float2bfloat16_rn(v4.x);
+    Vt[size_t(d4 + 1) * VP + j] = __float2bfloat16_rn(v4.y);
+    Vt[size_t(d4 + 2) * VP + j] = __float2bfloat16_rn(v4.z);
+    Vt[size_t(d4 + 3) * VP + j] = __float2bfloat16_rn(v4.w);
+  }
+  for (int j = threadIdx.x; j < kend; j += blockDim.x)
+    madd[j] = (j < S && (mask == nullptr || mask[row0 + j] != 0)) ? 0.f : -INFINITY;
+  __syncthreads();
+
+  const int i0 = q_lo + warp * 16;                // this warp's 16 query rows; thread owns rows i0 + g and i0 + g + 8
+  if (i0 >= S) return;
+  const int ra = i0 + g, rb = i0 + g + 8;
+  // ---- Q fragments (A operand, row-major 16 x DH): scaled in fp32, narrowed to bf16 ----
+  const float scale = rsqrtf(float(DH));
+  uint32_t qa[DH / 16][4];
+#pragma unroll
+  for (int ks = 0; ks < DH / 16; ++ks) {
+    const int c0 = ks * 16 + 2 * t;
+    const float* pa = qkv + (row0 + min(ra, S - 1)) * ld + h * DH + c0;
+    const float* pb = qkv + (row0 + min(rb, S - 1)) * ld + h * DH + c0;
+    const float2 a_lo = *reinterpret_cast<const float2*>(pa), a_hi = *reinterpret_cast<const float2*>(pa + 8);
+    const float2 b_lo = *reinterpret_cast<const float2*>(pb), b_hi = *reinterpret_cast<const float2*>(pb + 8);
+    qa[ks][0] = pack_bf16x2(a_lo.x * scale, a_lo.y * scale);
+    qa[ks][1] = pack_bf16x2(b_lo.x * scale, b_lo.y * scale);
+    qa[ks][2] = pack_bf16x2(a_hi.x * scale, a_hi.y * scale);
+    qa[ks][3] = pack_bf16x2(b_hi.x * scale, b_hi.y * scale);
+  }
+  float o[DH / 8][4];
+#pragma unroll
+  for (int dn = 0; dn < DH / 8; ++dn)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[dn][e] = 0.f;
+  float m_a = -INFINITY, m_b = -INFINITY, l_a = 0.f, l_b = 0.f;   // running max / (per-thread partial) sum of rows ra, rb
+
+  const int wend = causal ? min(kend, (min(i0 + 16, S) + ATC_KB - 1) / ATC_KB * ATC_KB) : kend;
+  for (int kb = 0; kb < wend; kb += ATC_KB) {
+    // S block = Q K^T: 16 rows x 64 keys = 8 n-tiles
+    float sc[ATC_KB / 8][4];
+#pragma unroll
+    for (int nt = 0; nt < ATC_KB / 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sc[nt][e] = 0.f;
+      const __nv_bfloat16* kr = Ks + size_t(kb + nt * 8 + g) * KP + 2 * t;
+#pragma unroll
+      for (int ks = 0; ks < DH / 16; ++ks) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + ks * 16);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8);
+        mma_bf16_16816(sc[nt], qa[ks], b0, b1);
+      }
+    }
+    // masks + block max (thread holds keys kb + nt*8 + 2t, +1 of rows ra (e = 0, 1) and rb (e = 2, 3))
+    float bm_a = -INFINITY, bm_b = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < ATC_KB / 8; ++nt) {
+      const int j = kb + nt * 8 + 2 * t;
+      const float2 ma = *reinterpret_cast<const float2*>(madd + j);
+      sc[nt][0] += ma.x;
+      sc[nt][1] += ma.y;
+      sc[nt][2] += ma.x;
+      sc[nt][3] += ma.y;
+      if (causal) {
+        if (j > ra) sc[nt][0] = -INFINITY;
+        if (j + 1 > ra) sc[nt][1] = -INFINITY;
+        if (j > rb) sc[nt][2] = -INFINITY;
+        if (j + 1 > rb) sc[nt][3] = -INFINITY;
+      }
+      bm_a = fmaxf(bm_a, fmaxf(sc[nt][0], sc[nt][1]));
+      bm_b = fmaxf(bm_b, fmaxf(sc[nt][2], sc[nt][3]));
+    }
+    bm_a = fmaxf(bm_a, __shfl_xor_sync(0xffffffffu, bm_a, 1));
+    bm_a = fmaxf(bm_a, __shfl_xor_sync(0xffffffffu, bm_a, 2));
+    bm_b = fmaxf(bm_b, __shfl_xor_sync(0xffffffffu, bm_b, 1));
+    bm_b = fmaxf(bm_b, __shfl_xor_sync(0xffffffffu, bm_b, 2));
+    const float mn_a = fmaxf(m_a, bm_a), mn_b = fmaxf(m_b, bm_b);
+    const float ms_a = mn_a == -INFINITY ? 0.f : mn_a, ms_b = mn_b == -INFINITY ? 0.f : mn_b;   // all masked so far: p = 0
+    const float f_a = __expf(m_a - ms_a), f_b = __expf(m_b - ms_b);                               // exp(-inf) = 0 on the first block
+    m_a = mn_a;
+    m_b = mn_b;
+    l_a *= f_a;
+    l_b *= f_b;
+#pragma unroll
+    for (int dn = 0; dn < DH / 8; ++dn) {
+      o[dn][0] *= f_a;
+      o[dn][1] *= f_a;
+      o[dn][2] *= f_b;
+      o[dn][3] *= f_b;
+    }
+#pragma unroll
+    for (int nt = 0; nt < ATC_KB / 8; ++nt) {
+      sc[nt][0] = __expf(sc[nt][0] - ms_a);
+      sc[nt][1] = __expf(sc[nt][1] - ms_a);
+      sc[nt][2] = __expf(sc[nt][2] - ms_b);
+      sc[nt][3] = __expf(sc[nt][3] - ms_b);
+      l_a += sc[nt][0] + sc[nt][1];
+      l_b += sc[nt][2] + sc[nt][3];
+    }
+    // O += P V: four k-steps of 16 keys; the A fragment of k-step kk is n-tiles 2kk, 2kk+1 of the score block
+#pragma unroll
+    for (int kk = 0; kk < ATC_KB / 16; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16x2(sc[2 * kk][0], sc[2 * kk][1]);
+      pa[1] = pack_bf16x2(sc[2 * kk][2], sc[2 * kk][3]);
+      pa[2] = pack_bf16x2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+      pa[3] = pack_bf16x2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+#pragma unroll
+      for (int dn = 0; dn < DH / 8; ++dn) {
+        const __nv_bfloat16* vr = Vt + size_t(dn * 8 + g) * VP + kb + kk * 16 + 2 * t;
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vr);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vr + 8);
+        mma_bf16_16816(o[dn], pa, b0, b1);
+      }
+    }
+  }
+  l_a += __shfl_xor_sync(0xffffffffu, l_a, 1);
+  l_a += __shfl_xor_sync(0xffffffffu, l_a, 2);
+  l_b += __shfl_xor_sync(0xffffffffu, l_b, 1);
+  l_b += __shfl_xor_sync(0xffffffffu, l_b, 2);
+  const float inv_a = l_a > 0.f ? 1.f / l_a : 0.f, inv_b = l_b > 0.f ? 1.f / l_b : 0.f;
+#pragma unroll
+  for (int dn = 0; dn < DH / 8; ++dn) {
+    const int c = h * DH + dn * 8 + 2 * t;
+    if (ra < S) *reinterpret_cast<uint32_t*>(ctx + (row0 + ra) * H + c) = pack_bf16x2(o[dn][0] * inv_a, o[dn][1] * inv_a);
+    if (rb < S) *reinterpret_cast<uint32_t*>(ctx + (row0 + rb) * H + c) = pack_bf16x2(o[dn][2] * inv_b, o[dn][3] * inv_b);
   }
 }
 

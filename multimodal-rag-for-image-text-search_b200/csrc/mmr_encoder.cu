@@ -307,8 +307,17 @@ static int forward_t(mmr_encoder* e, int B, int S, float* out_dev, cudaStream_t 
   if (!att_attr[dev & 63]) {
     CUDA_TRY(cudaFuncSetAttribute(attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(attention_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(attention_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     att_attr[dev & 63] = true;
   }
+  // the cross-encoder (rerank passages: 128-512 tokens) runs both attention contractions on the tensor cores, whatever the
+  // sequence length (kernel choice by model, never by batch shape); MMR_ENC_ATT_MMA=0: fp32 kernel everywhere, =2: every model
+  // from ATC_MIN_S tokens on (measurement)
+  const int att_opt = options().enc_att_mma;
+  const bool att_mma = att_opt == 2 ? S >= ATC_MIN_S : (att_opt == 1 && c.kind == MMR_ENC_CROSS);
+  const size_t att_mma_smem = DH == 32 ? attention_mma_smem_bytes<32>(S) : attention_mma_smem_bytes<64>(S);
+  const dim3 att_mma_grid(c.heads, B, (S + ATC_ROWS - 1) / ATC_ROWS);
   const size_t att_smem = DH == 32 ? attention_smem_bytes<32>(S) : attention_smem_bytes<64>(S);
   if (att_smem > 220 * 1024) return fail(MMR_ERR_UNSUPPORTED, "sequence length %d does not fit the attention kernel", S);
 
@@ -321,11 +330,10 @@ static int forward_t(mmr_encoder* e, int B, int S, float* out_dev, cudaStream_t 
     CUDA_TRY(launch_pdl(embed_kernel<H>, rows_grid, rows_block, 0, st, e->d_ids, e->d_types, e->word, e->pos, e->type_emb,
                         e->emb_ln_w, e->emb_ln_b, c.ln_eps, M, S, e->x, e->x16));
   mmr_g_launches++;
-  // LayerNorms in front of a GEMM are folded into it for a single short query (<= 16 tokens: one round of four tokens per
-  // epilogue warp).  Measured (profiles/r02_encoder_summary.md): 44 -> 33 / 86 -> 62 launches, MiniLM 1 x 16 unchanged, CLIP 1 x 16
-  // -5 %; from 128 tokens on the redundant per-CTA LayerNorm is slower than one layernorm_kernel launch (a dependent launch
-  // costs no more than the work it replaces), so larger passes keep the separate kernel.  MMR_ENC_FUSE_LN=0: never fold;
-  // =2: fold whenever the token tile is 64 (measurement).
+  // LayerNorms in front of a GEMM can be folded into it (MMR_ENC_FUSE_LN=1: passes of <= 16 tokens, =2: whenever the token
+  // tile is 64; bit-identical activations either way).  OFF by default -- measured (profiles/r02_encoder_summary.md): 44 -> 33 /
+  // 86 -> 62 launches buy nothing (MiniLM 1 x 16: 0.229 -> 0.259 ms, from 128 tokens on clearly slower): a dependent launch
+  // costs no more than the LayerNorm it carried, and every CTA of the GEMM repeats its token tile's LayerNorm.
   const int fuse_opt = options().enc_fuse_ln;
   const bool fuse_ln = fuse_opt == 2 ? enc_token_tile(M) == 64 : (fuse_opt == 1 && M <= 16);
   const LayerW* prev = nullptr;   // BERT: the layer whose closing LayerNorm (ln2 over e->tmp) is still pending
@@ -348,7 +356,13 @@ static int forward_t(mmr_encoder* e, int B, int S, float* out_dev, cudaStream_t 
       rc = launch_gemm<EPI_BIAS_F32>(L.m_qkv, e->m_x16, M, 3 * H, H, L.qkv_b, nullptr, e->qkv, nullptr, st);
     }
     if (rc != MMR_OK) return rc;
-    if (DH == 32)
+    if (att_mma && DH == 32)
+      CUDA_TRY(launch_pdl(attention_mma_kernel<32>, att_mma_grid, dim3(ATC_NW * 32), att_mma_smem, st, e->qkv, e->d_mask, e->ctx16, S,
+                          H, clip ? 1 : 0));
+    else if (att_mma)
+      CUDA_TRY(launch_pdl(attention_mma_kernel<64>, att_mma_grid, dim3(ATC_NW * 32), att_mma_smem, st, e->qkv, e->d_mask, e->ctx16, S,
+                          H, clip ? 1 : 0));
+    else if (DH == 32)
       CUDA_TRY(launch_pdl(attention_kernel<32>, dim3(c.heads, B), dim3(ATT_NW * 32), att_smem, st, e->qkv, e->d_mask, e->ctx16, S, H,
                           clip ? 1 : 0));
     else
