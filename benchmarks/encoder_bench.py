@@ -45,7 +45,13 @@ def main():
     shapes = {"minilm": [(1, 16), (8, 16), (32, 32), (128, 16)], "clip_text": [(1, 16), (8, 16), (128, 16), (32, 77)],
               "cross": [(8, 128), (64, 128), (8, 512)]}
     out = []
+    only = os.environ.get("ENC_BENCH_ONLY")              # e.g. "cross": one model family (A/B runs of a switch)
+    skip_torch = os.environ.get("ENC_BENCH_SKIP_TORCH") == "1"
+    if only == "cross":
+        shapes["cross"] = shapes["cross"] + [(16, 256), (128, 128), (32, 512)]
     for name, (model, fam) in models.items():
+        if only and name != only:
+            continue
         dev = enc_mod.DeviceEncoder.from_hf_bert(model) if fam == "bert" else enc_mod.DeviceEncoder.from_hf_clip(model)
         gpu32 = model.cuda()
         for b, s in shapes[name]:
@@ -58,6 +64,9 @@ def main():
             dev.forward_ids(ids, mask)
             launches = native.lib().mmr_launch_count() - n0
             ours = timed(lambda: dev.forward_ids(ids, mask))
+            if skip_torch:
+                out.append({"model": name, "batch": b, "seq": s, "device_encoder_ms": ours, "kernel_launches": int(launches)})
+                continue
             with torch.no_grad():
                 t32 = timed(lambda: gpu32(input_ids=ids_t, attention_mask=mask_t), reps=20)
                 with torch.autocast("cuda", dtype=torch.bfloat16):

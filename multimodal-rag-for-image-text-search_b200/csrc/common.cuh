@@ -64,6 +64,10 @@ struct Options {
   int enc_att_mma = 1;    // MMR_ENC_ATT_MMA     device encoders: 1 = the cross-encoder runs attention_mma_kernel (bf16 tensor-core
                           //                     contractions), the query encoders the fp32 kernel (default); 0 = fp32 everywhere;
                           //                     2 = every model from 96 tokens on (measurement)
+  int enc_gemm_smem_kb = 100;  // MMR_ENC_GEMM_SMEM_KB  shared-memory budget of one encoder GEMM CTA (ring depth).  100 lets two CTAs
+                               //                       share an SM, so one tile's epilogue (the bound: bias / GELU / residual over
+                               //                       NT columns per thread) overlaps the other's loads and MMAs: 128 x 128 rerank
+                               //                       pairs 1.99 -> 1.45 ms against 200 (profiles/r02_encoder_summary.md)
   int inline_query = 1;   // MMR_INLINE_QUERY=0  host-buffer calls always stage the query with an H2D copy (measurement)
   int mailbox = 0;        // MMR_MAILBOX=1       host-buffer calls spin on a flag the kernel writes into the mapped mailbox instead
                           //                     of synchronising the stream (measured no faster: profiles/r02_fixed_cost.json)

@@ -230,7 +230,7 @@ static int launch_gemm_nt(const CUtensorMap& mw, const CUtensorMap& mx, int M, i
   p.N = N;
   p.K = K;
   const int stage_bytes = ENC_W_SLICE + NT * 128;
-  p.nstages = std::min(std::min(ENC_MAX_STAGES, K / 64), (200 * 1024) / stage_bytes);
+  p.nstages = std::max(2, std::min(std::min(ENC_MAX_STAGES, K / 64), (options().enc_gemm_smem_kb * 1024) / stage_bytes));
   p.bias = bias;
   p.residual = residual;
   p.out_f32 = out_f32;
