@@ -59,7 +59,26 @@ __device__ __forceinline__ void tmem_alloc_cols(uint32_t dst_smem, uint32_t ncol
 __device__ __forceinline__ void tmem_dealloc_cols(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// GELU(erf): erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of the value it feeds) on the
+// approximate reciprocal / exp2 units -- the FFN1 epilogue is issue-bound on its four warps.  Measured per FFN1 launch at 16384
+// tokens (profiles/r02_encoder_summary.md): libm erff 74 us, this 0.97x of the whole pass; the same formula with IEEE
+// reciprocal and exp2f() 101 us.  -DMMR_ENC_LIBM_ERF restores erff.
+__device__ __forceinline__ float erf_as(float x) {
+  const float ax = fabsf(x);
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * ax * ax));
+  return copysignf(fmaf(-p * t, e, 1.0f), x);
+}
+#ifdef MMR_ENC_LIBM_ERF
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+#else
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f)); }
+#endif
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
 
 // out[t, f] = epilogue( sum_k X[t, k] * W[f, k] + bias[f] )      grid = (N / 128, ceil(M / NT))
@@ -512,22 +531,36 @@ __global__ void __launch_bounds__(ATC_NW * 32) attention_mma_kernel(const float*
   const int kend = causal ? min(sp, (min(q_lo + ATC_ROWS, S) + ATC_KB - 1) / ATC_KB * ATC_KB) : sp;   // keys this CTA can need
 
   // ---- stage K (row-major) and V (transposed) of this head as bf16, and the additive key mask ----
-  for (int i = threadIdx.x; i < kend * (DH / 4); i += blockDim.x) {
-    const int j = i / (DH / 4), d4 = (i % (DH / 4)) * 4;
-    float4 k4 = make_float4(0.f, 0.f, 0.f, 0.f), v4 = k4;
-    if (j < S) {
-      const float* src = qkv + (row0 + j) * ld + h * DH + d4;
-      k4 = *reinterpret_cast<const float4*>(src + H);
-      v4 = *reinterpret_cast<const float4*>(src + 2 * H);
+  // (four items per thread per round with all eight loads in flight before the first store: the loop is bound by the L2
+  //  round trip, not by bytes -- 16 dependent round trips per CTA at S = 512 in the first version)
+  for (int i0s = threadIdx.x; i0s < kend * (DH / 4); i0s += 4 * blockDim.x) {
+    float4 k4[4], v4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0s + u * blockDim.x;
+      const int j = i / (DH / 4), d4 = (i % (DH / 4)) * 4;
+      k4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      v4[u] = k4[u];
+      if (i < kend * (DH / 4) && j < S) {
+        const float* src = qkv + (row0 + j) * ld + h * DH + d4;
+        k4[u] = __ldcg(reinterpret_cast<const float4*>(src + H));
+        v4[u] = __ldcg(reinterpret_cast<const float4*>(src + 2 * H));
+      }
     }
-    uint2 kk;
-    kk.x = pack_bf16x2(k4.x, k4.y);
-    kk.y = pack_bf16x2(k4.z, k4.w);
-    *reinterpret_cast<uint2*>(Ks + size_t(j) * KP + d4) = kk;
-    Vt[size_t(d4 + 0) * VP + j] = __float2bfloat16_rn(v4.x);
-    Vt[size_t(d4 + 1) * VP + j] = __float2bfloat16_rn(v4.y);
-    Vt[size_t(d4 + 2) * VP + j] = __float2bfloat16_rn(v4.z);
-    Vt[size_t(d4 + 3) * VP + j] = __float2bfloat16_rn(v4.w);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0s + u * blockDim.x;
+      if (i >= kend * (DH / 4)) break;
+      const int j = i / (DH / 4), d4 = (i % (DH / 4)) * 4;
+      uint2 kk;
+      kk.x = pack_bf16x2(k4[u].x, k4[u].y);
+      kk.y = pack_bf16x2(k4[u].z, k4[u].w);
+      *reinterpret_cast<uint2*>(Ks + size_t(j) * KP + d4) = kk;
+      Vt[size_t(d4 + 0) * VP + j] = __float2bfloat16_rn(v4[u].x);
+      Vt[size_t(d4 + 1) * VP + j] = __float2bfloat16_rn(v4[u].y);
+      Vt[size_t(d4 + 2) * VP + j] = __float2bfloat16_rn(v4[u].z);
+      Vt[size_t(d4 + 3) * VP + j] = __float2bfloat16_rn(v4[u].w);
+    }
   }
   for (int j = threadIdx.x; j < kend; j += blockDim.x)
     madd[j] = (j < S && (mask == nullptr || mask[row0 + j] != 0)) ? 0.f : -INFINITY;
