@@ -50,6 +50,7 @@ struct Options {
   int umma_mode = 0;      // MMR_UMMA_MODE    0 = by batch size, 1 = ss, 2 = ts
   int umma_pair = 1;      // MMR_UMMA_PAIR=0  single CTAs instead of CTA pairs
   int umma_noprobe = 0;   // MMR_UMMA_NOPROBE=1
+  int umma_stages = 0;    // MMR_UMMA_STAGES=n   cap the single-CTA kernel's index ring at n 16 KB stages (measurement; 0 = as many as fit)
   int force_family = 0;   // MMR_FORCE_FAMILY 1 = K1, 2 = K2 regardless of batch size
   int umma_lockstep = 0;      // MMR_UMMA_LOCKSTEP=1  CTA pairs of one row slot keep within a window of tiles (measured SLOWER:
                               //                      profiles/r02_k2_summary.md; kept as a measurement switch)

@@ -472,7 +472,7 @@ inline int umma_search(UmmaIndexState& st, Umma2IndexState& st2, const void* row
     UmmaParams p{};
     p.ks = dim / 64;
     p.idesc = umma_idesc_m128_n128(dtype == MMR_BF16);
-    p.nstages = stages;
+    p.nstages = options().umma_stages >= 2 ? std::min(stages, options().umma_stages) : stages;   // MMR_UMMA_STAGES: ring depth cap (measurement)
     p.k = k;
     p.B = bq;
     p.row_begin = r0;
