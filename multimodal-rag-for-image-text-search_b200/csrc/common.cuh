@@ -69,6 +69,8 @@ struct Options {
                                //                       share an SM, so one tile's epilogue (the bound: bias / GELU / residual over
                                //                       NT columns per thread) overlaps the other's loads and MMAs: 128 x 128 rerank
                                //                       pairs 1.99 -> 1.45 ms against 200 (profiles/r02_encoder_summary.md)
+  int enc_narrow_tiles = 1;    // MMR_ENC_NARROW_TILES=0  encoder GEMMs: token tile by token count only (default: halved for the narrow
+                               //                         GEMMs until every SM has two CTAs)
   int inline_query = 1;   // MMR_INLINE_QUERY=0  host-buffer calls always stage the query with an H2D copy (measurement)
   int mailbox = 0;        // MMR_MAILBOX=1       host-buffer calls spin on a flag the kernel writes into the mapped mailbox instead
                           //                     of synchronising the stream (measured no faster: profiles/r02_fixed_cost.json)

@@ -110,6 +110,7 @@ static int* option_slot(const char* name) {
   if (!strcmp(name, "MMR_ENC_FUSE_LN")) return &o.enc_fuse_ln;
   if (!strcmp(name, "MMR_ENC_ATT_MMA")) return &o.enc_att_mma;
   if (!strcmp(name, "MMR_ENC_GEMM_SMEM_KB")) return &o.enc_gemm_smem_kb;
+  if (!strcmp(name, "MMR_ENC_NARROW_TILES")) return &o.enc_narrow_tiles;
   if (!strcmp(name, "MMR_INLINE_QUERY")) return &o.inline_query;
   if (!strcmp(name, "MMR_MAILBOX")) return &o.mailbox;
   return nullptr;
@@ -120,7 +121,7 @@ static int parse_option(const char* name, const char* v, int dflt) {
   return atoi(v);
 }
 static const char* kOptionNames[] = {"MMR_PDL", "MMR_UMMA_MODE", "MMR_UMMA_PAIR", "MMR_UMMA_NOPROBE", "MMR_FORCE_FAMILY",
-                                     "MMR_UMMA_LOCKSTEP", "MMR_INLINE_QUERY", "MMR_MAILBOX", "MMR_UMMA_SKIP_EPI", "MMR_UMMA_FUSED_PROBE", "MMR_ENC_FUSE_LN", "MMR_ENC_ATT_MMA", "MMR_ENC_GEMM_SMEM_KB", "MMR_UMMA_STAGES"};
+                                     "MMR_UMMA_LOCKSTEP", "MMR_INLINE_QUERY", "MMR_MAILBOX", "MMR_UMMA_SKIP_EPI", "MMR_UMMA_FUSED_PROBE", "MMR_ENC_FUSE_LN", "MMR_ENC_ATT_MMA", "MMR_ENC_GEMM_SMEM_KB", "MMR_UMMA_STAGES", "MMR_ENC_NARROW_TILES"};
 namespace {
 struct OptionsFromEnv {  // the environment is read once, when the library is loaded
   OptionsFromEnv() {

@@ -54,6 +54,8 @@ struct mmr_encoder {
   int32_t *d_ids = nullptr, *d_mask = nullptr, *d_types = nullptr, *h_stage = nullptr;
   CUtensorMap m_x16, m_ctx16, m_h16;
   int maps_tokens = -1;
+  int maps_narrow = -1;
+  int nt_x = 64, nt_ctx = 64, nt_h = 64;   // token tiles (= box rows) of the activation maps
 };
 
 static int dev_alloc(mmr_encoder* e, void** p, size_t bytes) {
@@ -218,6 +220,23 @@ static int ensure_arena(mmr_encoder* e, int tokens, int seqs) {
 }
 
 static int enc_token_tile(int M) { return M <= 1024 ? 64 : (M <= 4096 ? 128 : 256); }
+// Token tile of one GEMM: the M-based tile, halved while the grid (N / 128 feature tiles x token tiles) would leave SMs
+// without their two CTAs -- the narrow GEMMs (out-proj and FFN2: N = hidden = 3-4 feature tiles) ran 96 CTAs on 148 SMs at
+// 4096 tokens (profiles/r02_encoder_summary.md).  The tile never changes a result (accumulation runs along K only).
+static int enc_token_tile_for(int M, int N) {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  int nt = enc_token_tile(M);
+  if (options().enc_narrow_tiles == 0) return nt;
+  // 128 -> 64 until every SM has its two CTAs; 256 -> 128 only when SMs would otherwise idle (at 16384 tokens the 256-token
+  // tile with 192 CTAs beats 384 CTAs of 128: profiles/r02_encoder_summary.md)
+  while (nt > 64 && int64_t(N / ENC_BM) * ((M + nt - 1) / nt) < (nt == 256 ? 1 : 2) * int64_t(sms)) nt >>= 1;
+  return nt;
+}
 
 template <int EPI, int NT>
 static int launch_gemm_nt(const CUtensorMap& mw, const CUtensorMap& mx, int M, int N, int K, const float* bias,
@@ -246,9 +265,9 @@ static int launch_gemm_nt(const CUtensorMap& mw, const CUtensorMap& mx, int M, i
 }
 
 template <int EPI>
-static int launch_gemm(const CUtensorMap& mw, const CUtensorMap& mx, int M, int N, int K, const float* bias,
+static int launch_gemm(const CUtensorMap& mw, const CUtensorMap& mx, int nt, int M, int N, int K, const float* bias,
                        const float* residual, float* out_f32, __nv_bfloat16* out_bf16, cudaStream_t st) {
-  switch (enc_token_tile(M)) {
+  switch (nt) {   // = the box rows of the activation map mx
     case 64: return launch_gemm_nt<EPI, 64>(mw, mx, M, N, K, bias, residual, out_f32, out_bf16, st);
     case 128: return launch_gemm_nt<EPI, 128>(mw, mx, M, N, K, bias, residual, out_f32, out_bf16, st);
     default: return launch_gemm_nt<EPI, 256>(mw, mx, M, N, K, bias, residual, out_f32, out_bf16, st);
@@ -294,12 +313,17 @@ static int forward_t(mmr_encoder* e, int B, int S, float* out_dev, cudaStream_t 
   const bool clip = c.kind == MMR_ENC_CLIP_TEXT;
   const int wpb = 8;
   const dim3 rows_grid((M + wpb - 1) / wpb), rows_block(wpb * 32);
-  if (e->maps_tokens != M) {   // the activation maps depend on the live token count (TMA zero-fills rows past it)
-    const int nt = enc_token_tile(M);   // box rows of the activation maps = the GEMMs' token tile
-    if (!make_map(&e->m_x16, e->x16, M, H, nt) || !make_map(&e->m_ctx16, e->ctx16, M, H, nt) ||
-        !make_map(&e->m_h16, e->h16, M, I, nt))
+  if (e->maps_tokens != M || e->maps_narrow != options().enc_narrow_tiles) {   // the activation maps depend on the live token count (TMA zero-fills rows past it)
+    // box rows of an activation map = the token tile of the GEMMs that read it: x16 feeds QKV (N = 3H) and FFN1 (N = I),
+    // ctx16 the out-projection and h16 FFN2 (both N = H)
+    e->nt_x = enc_token_tile_for(M, std::min(3 * H, I));
+    e->nt_ctx = enc_token_tile_for(M, H);
+    e->nt_h = enc_token_tile_for(M, H);
+    if (!make_map(&e->m_x16, e->x16, M, H, e->nt_x) || !make_map(&e->m_ctx16, e->ctx16, M, H, e->nt_ctx) ||
+        !make_map(&e->m_h16, e->h16, M, I, e->nt_h))
       return fail(MMR_ERR_CUDA, "cuTensorMapEncodeTiled failed for the activations");
     e->maps_tokens = M;
+    e->maps_narrow = options().enc_narrow_tiles;
   }
   static bool att_attr[64] = {};
   int dev = 0;
@@ -347,13 +371,13 @@ static int forward_t(mmr_encoder* e, int B, int S, float* out_dev, cudaStream_t 
         CUDA_TRY(launch_pdl(layernorm_kernel<H>, rows_grid, rows_block, 0, st, e->x, L.ln1_w, L.ln1_b, c.ln_eps, M,
                             (float*)nullptr, e->x16));
         mmr_g_launches++;
-        rc = launch_gemm<EPI_BIAS_F32>(L.m_qkv, e->m_x16, M, 3 * H, H, L.qkv_b, nullptr, e->qkv, nullptr, st);
+        rc = launch_gemm<EPI_BIAS_F32>(L.m_qkv, e->m_x16, e->nt_x, M, 3 * H, H, L.qkv_b, nullptr, e->qkv, nullptr, st);
       }
     } else if (prev != nullptr) {   // BERT, fused: x = LN2_prev(tmp) computed by this layer's QKV GEMM
       rc = launch_gemm_ln<EPI_BIAS_F32>(L.m_qkv, e->m_x16, M, 3 * H, H, L.qkv_b, e->qkv, nullptr, e->tmp, prev->ln2_w, prev->ln2_b,
                                         c.ln_eps, e->x, st);
     } else {
-      rc = launch_gemm<EPI_BIAS_F32>(L.m_qkv, e->m_x16, M, 3 * H, H, L.qkv_b, nullptr, e->qkv, nullptr, st);
+      rc = launch_gemm<EPI_BIAS_F32>(L.m_qkv, e->m_x16, e->nt_x, M, 3 * H, H, L.qkv_b, nullptr, e->qkv, nullptr, st);
     }
     if (rc != MMR_OK) return rc;
     if (att_mma && DH == 32)
@@ -371,7 +395,7 @@ static int forward_t(mmr_encoder* e, int B, int S, float* out_dev, cudaStream_t 
     mmr_g_launches++;
     if (clip) {
       // x = x + out_proj(ctx); h = LN2(x); x = x + fc2(quick_gelu(fc1(h)))
-      rc = launch_gemm<EPI_BIAS_RES_F32>(L.m_o, e->m_ctx16, M, H, H, L.o_b, e->x, e->x, nullptr, st);
+      rc = launch_gemm<EPI_BIAS_RES_F32>(L.m_o, e->m_ctx16, e->nt_ctx, M, H, H, L.o_b, e->x, e->x, nullptr, st);
       if (rc != MMR_OK) return rc;
       if (fuse_ln) {
         rc = launch_gemm_ln<EPI_QUICKGELU_BF16>(L.m_fc1, e->m_x16, M, I, H, L.fc1_b, nullptr, e->h16, e->x, L.ln2_w, L.ln2_b, c.ln_eps,
@@ -380,14 +404,14 @@ static int forward_t(mmr_encoder* e, int B, int S, float* out_dev, cudaStream_t 
         CUDA_TRY(launch_pdl(layernorm_kernel<H>, rows_grid, rows_block, 0, st, e->x, L.ln2_w, L.ln2_b, c.ln_eps, M,
                             (float*)nullptr, e->x16));
         mmr_g_launches++;
-        rc = launch_gemm<EPI_QUICKGELU_BF16>(L.m_fc1, e->m_x16, M, I, H, L.fc1_b, nullptr, nullptr, e->h16, st);
+        rc = launch_gemm<EPI_QUICKGELU_BF16>(L.m_fc1, e->m_x16, e->nt_x, M, I, H, L.fc1_b, nullptr, nullptr, e->h16, st);
       }
       if (rc != MMR_OK) return rc;
-      rc = launch_gemm<EPI_BIAS_RES_F32>(L.m_fc2, e->m_h16, M, H, I, L.fc2_b, e->x, e->x, nullptr, st);
+      rc = launch_gemm<EPI_BIAS_RES_F32>(L.m_fc2, e->m_h16, e->nt_h, M, H, I, L.fc2_b, e->x, e->x, nullptr, st);
       if (rc != MMR_OK) return rc;
     } else {
       // post-LN (BERT): x = LN1(x + out_proj(ctx)); x = LN2(x + fc2(gelu(fc1(x))))
-      rc = launch_gemm<EPI_BIAS_RES_F32>(L.m_o, e->m_ctx16, M, H, H, L.o_b, e->x, e->tmp, nullptr, st);
+      rc = launch_gemm<EPI_BIAS_RES_F32>(L.m_o, e->m_ctx16, e->nt_ctx, M, H, H, L.o_b, e->x, e->tmp, nullptr, st);
       if (rc != MMR_OK) return rc;
       if (fuse_ln) {
         rc = launch_gemm_ln<EPI_GELU_BF16>(L.m_fc1, e->m_x16, M, I, H, L.fc1_b, nullptr, e->h16, e->tmp, L.ln1_w, L.ln1_b, c.ln_eps,
@@ -395,10 +419,10 @@ static int forward_t(mmr_encoder* e, int B, int S, float* out_dev, cudaStream_t 
       } else {
         CUDA_TRY(launch_pdl(layernorm_kernel<H>, rows_grid, rows_block, 0, st, e->tmp, L.ln1_w, L.ln1_b, c.ln_eps, M, e->x, e->x16));
         mmr_g_launches++;
-        rc = launch_gemm<EPI_GELU_BF16>(L.m_fc1, e->m_x16, M, I, H, L.fc1_b, nullptr, nullptr, e->h16, st);
+        rc = launch_gemm<EPI_GELU_BF16>(L.m_fc1, e->m_x16, e->nt_x, M, I, H, L.fc1_b, nullptr, nullptr, e->h16, st);
       }
       if (rc != MMR_OK) return rc;
-      rc = launch_gemm<EPI_BIAS_RES_F32>(L.m_fc2, e->m_h16, M, H, I, L.fc2_b, e->x, e->tmp, nullptr, st);
+      rc = launch_gemm<EPI_BIAS_RES_F32>(L.m_fc2, e->m_h16, e->nt_h, M, H, I, L.fc2_b, e->x, e->tmp, nullptr, st);
       if (rc != MMR_OK) return rc;
       if (fuse_ln && &L != &e->layers.back()) {
         prev = &L;   // LN2 rides in the next layer's QKV GEMM
