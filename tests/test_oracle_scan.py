@@ -71,3 +71,27 @@ def test_oracle_store_roundtrip():
     assert all(h["meta"]["i"] % 2 == 1 for h in hits)
     assert store.search_text("nobody", rows[5].embedding, 3) == []
     assert len(store.search_text("u1", rows[5].embedding, 0)) == 1
+
+
+def test_oracle_agrees_with_an_independent_bruteforce_cosine_knn():
+    """Second opinion on the scan oracle (still not LanceDB, which is not installable here): scikit-learn's exact
+    brute-force cosine KNN -- an unrelated implementation of "d = 1 - cos, k smallest" -- must return the same ids
+    (tie-aware) and distances within fp32 rounding, on unit and non-unit rows, inside a tenant range, for k = 10 and 50."""
+    sk = pytest.importorskip("sklearn.neighbors")
+    rng = np.random.default_rng(12)
+    for dim, n, unit in ((384, 4000, True), (512, 3000, False)):
+        rows = util.unit_rows(n, dim, 20 + dim)
+        if not unit:
+            rows = (rows * rng.uniform(0.5, 2.0, size=(n, 1))).astype(np.float32)
+        qs = util.queries(6, dim, seed=30 + dim) * 2.5
+        lo, hi = 500, n - 700
+        nn = sk.NearestNeighbors(metric="cosine", algorithm="brute").fit(rows[lo:hi].astype(np.float64))
+        for k in (10, 50):
+            dist, idx = nn.kneighbors(qs.astype(np.float64), n_neighbors=k)
+            for j in range(len(qs)):
+                d, ids = ofs.flat_search(rows, qs[j], k, lo=lo, hi=hi, unit_rows=unit)
+                assert np.abs(d - dist[j]).max() < 2e-6
+                want = idx[j] + lo
+                for p in range(k):
+                    if ids[p] != want[p]:      # only inside a run of (near-)equal distances
+                        assert abs(dist[j][p] - d[p]) < 2e-6 and ids[p] in want and want[p] in ids, (dim, k, j, p)
