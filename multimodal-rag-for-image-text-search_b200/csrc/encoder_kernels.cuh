@@ -483,8 +483,8 @@ __global__ void __launch_bounds__(ATT_NW * 32) attention_kernel(const float* __r
 // runs both contractions on the tensor cores, flash-attention style, with warp-level mma.sync m16n8k16 (bf16 in, fp32
 // accumulate): the natural tile for head dim 32 / 64 -- a tcgen05 tile is 128 rows with the accumulator in tensor memory,
 // and the online softmax between the two contractions would cross TMEM <-> registers twice per key block for a layer whose
-// total work is 3 GFLOP.  grid = (heads, B, ceil(S / 128)); a CTA = 8 warps x 16 query rows; K [S][DH] and V^T [DH][S] of
-// the head live in shared memory as bf16 (row pads make every fragment load conflict-free); scores never leave registers:
+// total work is 3 GFLOP.  grid = (heads, B, ceil(S / 128)); a CTA = 8 warps x 16 query rows; K and V [S][DH] of the
+// head live in shared memory as bf16 (row pads make every ldmatrix conflict-free; V is transposed by ldmatrix.trans); scores never leave registers:
 // per 64-key block S = Q K^T (fp32 accumulators), running max / sum, P packed to bf16 straight from the accumulator
 // registers (the m16n8 C layout IS the m16n8k16 A layout), O += P V.  Q is scaled in fp32 before narrowing.
 // Used for the cross-encoder (every sequence length: which kernel runs must not depend on what a pair is batched with; a
@@ -498,13 +498,24 @@ constexpr int ATC_MIN_S = 96;           // MMR_ENC_ATT_MMA=2 (measurement): ever
 template <int DH>
 inline size_t attention_mma_smem_bytes(int S) {
   const int sp = (S + ATC_KB - 1) / ATC_KB * ATC_KB;
-  return size_t(sp) * (DH + 8) * 2 + size_t(DH) * (sp + 8) * 2 + size_t(sp) * 4;
+  return size_t(sp) * (DH + 8) * 2 * 2 + size_t(sp) * 4;   // K and V [sp][DH + 8] bf16, additive key mask
 }
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// four 8 x 8 b16 matrices; lane i supplies the address of row (i % 8) of matrix (i / 8).  Plain: thread T gets
+// M[T / 4][2 (T % 4) .. +1]; .trans: M[2 (T % 4) .. +1][T / 4] -- exactly the m16n8k16 B fragments of a [key][dim] tile for
+// Q K^T (plain: k = dim) and for P V (.trans: k = key).
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);   // .x (low half) = lo
@@ -518,10 +529,9 @@ __global__ void __launch_bounds__(ATC_NW * 32) attention_mma_kernel(const float*
   pdl_chain_prologue();
   constexpr int KP = DH + 8;                      // K row pitch (bf16): 80 / 144 bytes -> the 8 rows of a fragment hit 8 bank groups
   const int sp = (S + ATC_KB - 1) / ATC_KB * ATC_KB;
-  const int VP = sp + 8;                          // V^T row pitch (bf16)
   __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(atc_smem);                 // [sp][KP]
-  __nv_bfloat16* Vt = Ks + size_t(sp) * KP;                                       // [DH][VP]
-  float* madd = reinterpret_cast<float*>(Vt + size_t(DH) * VP);                   // [sp] 0 or -inf (padding keys, keys >= S)
+  __nv_bfloat16* Vs = Ks + size_t(sp) * KP;                                       // [sp][KP] (row-major: ldmatrix.trans transposes)
+  float* madd = reinterpret_cast<float*>(Vs + size_t(sp) * KP);                   // [sp] 0 or -inf (padding keys, keys >= S)
   const int h = blockIdx.x, b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -556,16 +566,17 @@ __global__ void __launch_bounds__(ATC_NW * 32) attention_mma_kernel(const float*
       kk.x = pack_bf16x2(k4[u].x, k4[u].y);
       kk.y = pack_bf16x2(k4[u].z, k4[u].w);
       *reinterpret_cast<uint2*>(Ks + size_t(j) * KP + d4) = kk;
-      Vt[size_t(d4 + 0) * VP + j] = __float2bfloat16_rn(v4[u].x);
-      Vt[size_t(d4 + 1) * VP + j] = __float2bfloat16_rn(v4[u].y);
-      Vt[size_t(d4 + 2) * VP + j] = __float2bfloat16_rn(v4[u].z);
-      Vt[size_t(d4 + 3) * VP + j] = __float2bfloat16_rn(v4[u].w);
+      uint2 vv;
+      vv.x = pack_bf16x2(v4[u].x, v4[u].y);
+      vv.y = pack_bf16x2(v4[u].z, v4[u].w);
+      *reinterpret_cast<uint2*>(Vs + size_t(j) * KP + d4) = vv;
     }
   }
   for (int j = threadIdx.x; j < kend; j += blockDim.x)
     madd[j] = (j < S && (mask == nullptr || mask[row0 + j] != 0)) ? 0.f : -INFINITY;
   __syncthreads();
 
+  const uint32_t ks_base = smem_u32(Ks), vs_base = smem_u32(Vs);
   const int i0 = q_lo + warp * 16;                // this warp's 16 query rows; thread owns rows i0 + g and i0 + g + 8
   if (i0 >= S) return;
   const int ra = i0 + g, rb = i0 + g + 8;
@@ -599,12 +610,14 @@ __global__ void __launch_bounds__(ATC_NW * 32) attention_mma_kernel(const float*
     for (int nt = 0; nt < ATC_KB / 8; ++nt) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) sc[nt][e] = 0.f;
-      const __nv_bfloat16* kr = Ks + size_t(kb + nt * 8 + g) * KP + 2 * t;
+      // lane i -> row (i % 8) of the n-tile's keys, dims (i / 8) * 8 .. +7 of a 32-dim half: one ldmatrix = two k-steps
+      const uint32_t kaddr = ks_base + uint32_t((kb + nt * 8 + (lane & 7)) * KP + (lane >> 3) * 8) * 2u;
 #pragma unroll
-      for (int ks = 0; ks < DH / 16; ++ks) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + ks * 16);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8);
-        mma_bf16_16816(sc[nt], qa[ks], b0, b1);
+      for (int kh = 0; kh < DH / 32; ++kh) {
+        uint32_t kf[4];
+        ldmatrix_x4(kf, kaddr + kh * 64);
+        mma_bf16_16816(sc[nt], qa[2 * kh], kf[0], kf[1]);
+        mma_bf16_16816(sc[nt], qa[2 * kh + 1], kf[2], kf[3]);
       }
     }
     // masks + block max (thread holds keys kb + nt*8 + 2t, +1 of rows ra (e = 0, 1) and rb (e = 2, 3))
@@ -661,12 +674,14 @@ __global__ void __launch_bounds__(ATC_NW * 32) attention_mma_kernel(const float*
       pa[1] = pack_bf16x2(sc[2 * kk][2], sc[2 * kk][3]);
       pa[2] = pack_bf16x2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
       pa[3] = pack_bf16x2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+      // lane i -> key kb + 16 kk + (i / 8 % 2) * 8 + i % 8, dims (dn + i / 16) * 8 .. +7: {b0, b1} of dn and of dn + 1
+      const uint32_t vaddr = vs_base + uint32_t((kb + kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * KP + (lane >> 4) * 8) * 2u;
 #pragma unroll
-      for (int dn = 0; dn < DH / 8; ++dn) {
-        const __nv_bfloat16* vr = Vt + size_t(dn * 8 + g) * VP + kb + kk * 16 + 2 * t;
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vr);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vr + 8);
-        mma_bf16_16816(o[dn], pa, b0, b1);
+      for (int dn = 0; dn < DH / 8; dn += 2) {
+        uint32_t vf[4];
+        ldmatrix_x4_trans(vf, vaddr + dn * 16);
+        mma_bf16_16816(o[dn], pa, vf[0], vf[1]);
+        mma_bf16_16816(o[dn + 1], pa, vf[2], vf[3]);
       }
     }
   }
