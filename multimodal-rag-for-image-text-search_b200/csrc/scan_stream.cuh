@@ -8,8 +8,8 @@
 //   * persistent grid, one CTA per SM, NW consumer warps per CTA;
 //   * every warp owns a private ring of S stages in shared memory.  One stage = R consecutive index rows
 //     (R * D * sizeof(elem) contiguous bytes), filled by ONE 1-D bulk async copy (cp.async.bulk, the TMA
-//     engine without a descriptor) that signals an mbarrier.  NW * S stages (~192 KB/SM) are in flight,
-//     independent of register pressure;
+//     engine without a descriptor) that signals an mbarrier.  NW * S stages are in flight, independent of register
+//     pressure (tuned geometry below: 8 warps x 2 stages x 4 rows = 64 KB per SM for one query; deeper / wider for groups);
 //   * chunk c of the row range goes to global warp (c mod total_warps): at any instant the chip reads
 //     one contiguous window of HBM;
 //   * per stage a warp computes R x NQ dot products: lane l holds 8/16-byte column slices of each row and
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__((StreamCfg<E, D, NQ, KPL>::THREADS), 1) scan_s
   } else {
     // ------------------------------ varlen mode ------------------------------
     // An item is one piece of one row range scanned for up to NQ queries that share it (the queries of one tenant in this
-    // batch, grouped by the host planner: the rows are read once for the group).  The eight warps of the CTA interleave the
+    // batch, grouped by the host planner: the rows are read once for the group).  The warps of the CTA interleave the
     // item's chunks exactly as in uniform mode, so the CTA streams ONE contiguous window of HBM (per-warp items made every
     // warp stream its own distant region).  Items are claimed DYNAMICALLY: the host sorts them by size, largest first, CTA c
     // starts with item c and then takes the next unclaimed one (atomic counter, claimed one item ahead so the latency hides
