@@ -141,7 +141,9 @@ class HostTable:
                 hit = None
             else:
                 bufs = arr.buffers()
-                off = np.frombuffer(bufs[1], dtype=np.int32, count=len(arr) + 1, offset=arr.offset * 4)
+                # offsets as a memoryview of C ints: indexing yields Python ints directly (a numpy scalar per offset made
+                # the ten lookups of a result list cost ~20 us)
+                off = memoryview(bufs[1])[arr.offset * 4:(arr.offset + len(arr) + 1) * 4].cast("i")
                 hit = (off, memoryview(bufs[2]) if bufs[2] is not None else memoryview(b""))
             cache[col] = hit
         return hit
@@ -169,6 +171,41 @@ class HostTable:
                 off, data = raw
                 out.append(str(data[off[j]:off[j + 1]], "utf-8"))
         return out
+
+    def hits_at(self, rows: Sequence[int]) -> Tuple[list, list]:
+        """(chunk ids, parsed meta dicts) of a result list's host rows in ONE pass over the Arrow buffers; the empty meta
+        ("{}" / "" / null -- what ingest writes for most chunks) is recognised on its raw bytes without decoding or parsing
+        (reference _format_results, lancedb_store.py:125-139: json.loads(meta) if meta else {})."""
+        import bisect
+        import json
+
+        ids, metas = [], []
+        starts = self._starts_list
+        single = len(self.blocks) == 1
+        last_b, blk, raw_id, raw_meta, start = -1, None, None, None, 0
+        for r in rows:
+            r = int(r)
+            b = 0 if single else bisect.bisect_right(starts, r) - 1
+            if b != last_b:
+                blk = self.blocks[b]
+                raw_id, raw_meta, start, last_b = self._raw(blk, "chunk_id"), self._raw(blk, "meta"), blk.start, b
+            j = r - start
+            if raw_id is None:
+                ids.append(blk.cols["chunk_id"][j].as_py())
+            else:
+                off, data = raw_id
+                ids.append(str(data[off[j]:off[j + 1]], "utf-8"))
+            if raw_meta is None:
+                m = blk.cols["meta"][j].as_py()
+                metas.append({} if m in (None, "", "{}") else json.loads(m))
+            else:
+                off, data = raw_meta
+                a, e = off[j], off[j + 1]
+                if e == a or (e - a == 2 and data[a] == 123 and data[a + 1] == 125):   # "" or "{}" (byte tests: comparing a
+                    metas.append({})                                                   # memoryview with bytes is slow)
+                else:
+                    metas.append(json.loads(str(data[a:e], "utf-8")))
+        return ids, metas
 
     def gather(self, rows: np.ndarray) -> np.ndarray:
         """f32 embeddings of the given host rows (any order), O(len(rows))."""

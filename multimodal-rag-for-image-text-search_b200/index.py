@@ -49,6 +49,7 @@ class ResidentIndex:
         self.seg_offsets = None if seg_offsets is None else np.ascontiguousarray(seg_offsets, dtype=np.int64)
         self._handle = C.c_void_p()
         self._ws: Optional[torch.Tensor] = None
+        self._one: dict = {}     # search_host_one: per-k cached output arrays + their addresses
         self._ws_key = (0, 0, 0)
         lib = N.lib()
         nseg = 0 if self.seg_offsets is None else len(self.seg_offsets) - 1
@@ -243,6 +244,31 @@ class ResidentIndex:
             with torch.cuda.device(self.device):
                 N.check(N.lib().mmr_search_host(self._handle, q.ctypes.data, None if seg_arr is None else seg_arr.ctypes.data,
                                                 b, k, scores.ctypes.data, rows.ctypes.data, _stream_ptr(self.device)))
+        return scores, rows
+
+
+    def search_host_one(self, q: np.ndarray, k: int, segment: int = 0):
+        """The single-request form of search_host for the serving store: `q` is ONE query, float32, C-contiguous, [1, dim] or
+        [dim].  The output arrays and the segment word are cached per k and REUSED by the next call (the caller holds the
+        collection lock and converts them before it releases it), so a request allocates nothing and builds no ctypes
+        views: ~5 us less host work per call than search_host."""
+        k = max(int(k), 1)
+        slot = self._one.get(k)
+        if slot is None:
+            scores = np.empty((1, k), dtype=np.float32)
+            rows = np.empty((1, k), dtype=np.int64)
+            seg = np.zeros(1, dtype=np.int32)
+            slot = self._one[k] = (scores, rows, seg, scores.ctypes.data, rows.ctypes.data, seg.ctypes.data)
+        scores, rows, seg, p_s, p_r, p_seg = slot
+        if q.dtype != np.float32 or not q.flags.c_contiguous or q.size != self.dim:
+            raise ValueError(f"search_host_one needs one contiguous float32 query of dim {self.dim}")
+        seg[0] = segment
+        fn = N.lib().mmr_search_host
+        if torch.cuda.current_device() == (self.device.index or 0):
+            N.check(fn(self._handle, q.ctypes.data, p_seg, 1, k, p_s, p_r, _stream_ptr(self.device)))
+        else:
+            with torch.cuda.device(self.device):
+                N.check(fn(self._handle, q.ctypes.data, p_seg, 1, k, p_s, p_r, _stream_ptr(self.device)))
         return scores, rows
 
 

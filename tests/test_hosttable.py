@@ -56,6 +56,28 @@ def test_append_replace_and_duplicates_inside_a_batch():
         t.append_table(_table(["x"], ["u"], dim=4)[0])
 
 
+def test_hits_at_reads_ids_and_metas_of_a_result_list_in_one_pass():
+    """HostTable.hits_at = what _format_results needs per hit (chunk_id, json.loads(meta) if meta else {}), straight out of
+    the Arrow buffers: empty metas recognised on their raw bytes, rows spread over several blocks, sliced tables, and a
+    block whose meta column has nulls (slow path through Arrow scalars)."""
+    import pyarrow as pa
+    t = ht.HostTable("text_collection")
+    metas1 = ["{}", "", '{"page": 3, "t": "x y"}', "{}", '{"a": [1, 2]}', "[]"]
+    tab1, _ = _table([f"a{i}" for i in range(6)], ["u"] * 6, metas=metas1)
+    t.append_table(tab1)
+    tab2, _ = _table([f"b{i}" for i in range(40)], ["v"] * 40, seed=1, metas=['{"i": %d}' % i for i in range(40)])
+    t.append_table(tab2.slice(5, 20))                                   # a sliced table: the offsets buffer carries an offset
+    tab3, _ = _table(["c0", "c1", "c2"], ["w"] * 3, seed=2)
+    tab3 = tab3.set_column(tab3.schema.get_field_index("meta"), "meta", pa.array(['{"k": 1}', None, "{}"], pa.string()))
+    t.append_table(tab3)
+    rows = [2, 0, 1, 5, 4, 3, 6, 25, 10, 26, 27, 28]
+    ids, metas = t.hits_at(rows)
+    assert ids == ["a2", "a0", "a1", "a5", "a4", "a3", "b5", "b24", "b9", "c0", "c1", "c2"]
+    assert metas == [{"page": 3, "t": "x y"}, {}, {}, [], {"a": [1, 2]}, {}, {"i": 5}, {"i": 24}, {"i": 9}, {"k": 1}, {}, {}]
+    assert ids == t.values_at("chunk_id", rows)
+    assert t.hits_at([]) == ([], [])
+
+
 def test_index_levels_merge_and_million_row_table_stays_columnar():
     """1M rows in one bulk append, then small upserts: no per-row Python objects, lookups through the sorted hash index."""
     import pyarrow as pa
