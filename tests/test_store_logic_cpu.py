@@ -107,3 +107,19 @@ def test_persist_and_reload(cpu_store, tmp_path):
     assert table.schema.names == ["chunk_id", "user_id", "document_id", "modality", "embedding", "meta"]
     s2.load_arrow("text_collection", table)
     assert s2.search_text("u", [1.0] * 384, 1)[0]["chunk_id"] == "x"
+
+
+def test_query_row_narrows_a_python_list_exactly_like_numpy():
+    """_query_row: the reference hands search_* a Python list of floats (retrieve.py:53,84); the C-level narrowing must give
+    the float32 values np.asarray(list, float32) gives, for floats, ints, numpy scalars, tuples and arrays, and must fall
+    back to numpy for anything array('f') refuses."""
+    rng = np.random.default_rng(3)
+    vals = (rng.standard_normal(384) * 10.0 ** rng.integers(-6, 6, 384)).tolist() + [0.0, -0.0, 1, -7, 1 / 3, 16777217.0]
+    for src in (vals, tuple(vals), [np.float32(v) for v in vals[:50]], np.asarray(vals), np.asarray(vals, dtype=np.float32)):
+        got = store_mod._query_row(src)
+        want = np.asarray(src, dtype=np.float32)[None, :]
+        assert got.dtype == np.float32 and got.shape == want.shape and got.flags.c_contiguous
+        assert got.tobytes() == want.tobytes()
+    assert store_mod._query_row([]).shape == (1, 0)
+    odd = store_mod._query_row([0.1, None, 0.3])          # array('f') refuses None: numpy's answer (nan) through the fallback
+    assert odd.shape == (1, 3) and np.isnan(odd[0, 1]) and odd[0, 0] == np.float32(0.1)
